@@ -1,0 +1,313 @@
+// algo_bfs.cu -- level-only BFS as push/pull structural SpMV with a direction
+// switch.  Replaces LA_BFS (bfs.cpp:70-83) -> LAGr_BreadthFirstSearch(&level,
+// NULL, G, src): level[src] = 0, no entry (GX_UNREACHED_LEVEL) when unreached.
+// Levels are identical whichever direction a level is expanded in, so the
+// switch is a pure performance decision (LAGraph's own push/pull rule, which
+// the reference's wrapper disables by not caching AT, bfs.cpp:79-80).
+//
+//   push (sparse frontier queue, out-edges): warp per frontier vertex, hubs
+//        re-queued as CHUNK-entry pieces for whole CTAs; atomicCAS claims
+//        a vertex, warp-ballot compaction appends it to the next queue
+//   pull (bitmap frontier, in-edges): thread per unvisited vertex, early exit
+//        on the first parent in the frontier bitmap; one warp owns one
+//        32-vertex bitmap word, written with a ballot (no atomics); rows longer
+//        than ROW_SPLIT go to a warp-per-row kernel
+// Algorithmic bytes (one-pass bound): 4 m_reach + 8(n+1) + 4n + 2 (n/8) levels.
+#include "graph.cuh"
+
+namespace gx {
+
+constexpr int32_t UNVIS = -1;
+constexpr uint32_t PUSH_BIG = 4096; // frontier vertices with more out-edges are chunked
+
+struct BfsCounters { unsigned long long nf, mf, next_count, big_count; };
+
+__global__ void k_bfs_seed(int32_t *level, uint32_t *queue, uint32_t src)
+{
+    level[src] = 0;
+    queue[0] = src;
+}
+
+// claim v for `depth`; returns true for the unique winner
+__device__ __forceinline__ bool bfs_claim(int32_t *level, uint32_t v, int32_t depth)
+{
+    if (level[v] != UNVIS) return false;
+    return atomicCAS(&level[v], UNVIS, depth) == UNVIS;
+}
+
+// warp-aggregated append of the winners of one 32-lane step
+__device__ __forceinline__ void bfs_append(bool won, uint32_t v, uint32_t *next_q, BfsCounters *cnt)
+{
+    unsigned mask = __ballot_sync(FULL, won);
+    if (mask == 0) return;
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(&cnt->next_count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(FULL, base, 0);
+    if (won) next_q[base + __popc(mask & ((1u << lane_id()) - 1u))] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_bfs_push(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ queue,
+           uint64_t qn, int32_t *__restrict__ level, int32_t depth, uint32_t *__restrict__ next_q,
+           uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, BfsCounters *__restrict__ cnt)
+{
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long nf = 0, mf = 0;
+    for (; wid < qn; wid += nw) {
+        const uint32_t u = queue[wid];
+        const uint64_t a = rowptr[u], b = rowptr[u + 1];
+        if (b - a > PUSH_BIG) {
+            const uint64_t nch = (b - a + CHUNK - 1) / CHUNK;
+            unsigned long long pos = 0;
+            if (lane_id() == 0) pos = atomicAdd(&cnt->big_count, (unsigned long long)nch);
+            pos = __shfl_sync(FULL, pos, 0);
+            for (uint64_t k = lane_id(); k < nch; k += 32) { big_row[pos + k] = u; big_begin[pos + k] = a + k * CHUNK; }
+            continue;
+        }
+        for (uint64_t base = a; base < b; base += 32) {
+            const uint64_t e = base + lane_id();
+            bool won = false;
+            uint32_t v = 0;
+            if (e < b) {
+                v = ld_stream(col + e);
+                won = bfs_claim(level, v, depth);
+                if (won) { nf++; mf += rowptr[v + 1] - rowptr[v]; }
+            }
+            bfs_append(won, v, next_q, cnt);
+        }
+    }
+    nf = warp_sum(nf);
+    mf = warp_sum(mf);
+    if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
+}
+
+__global__ void __launch_bounds__(256)
+k_bfs_push_big(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ big_row,
+               const uint64_t *__restrict__ big_begin, int32_t *__restrict__ level, int32_t depth,
+               uint32_t *__restrict__ next_q, BfsCounters *__restrict__ cnt)
+{
+    const unsigned long long nbig = cnt->big_count;
+    unsigned long long nf = 0, mf = 0;
+    for (unsigned long long c = blockIdx.x; c < nbig; c += gridDim.x) {
+        const uint64_t b0 = big_begin[c];
+        const uint64_t row_end = rowptr[big_row[c] + 1];
+        const uint64_t e_end = (b0 + CHUNK < row_end) ? b0 + CHUNK : row_end;
+        for (uint64_t base = b0; base < e_end; base += 256) {
+            const uint64_t e = base + threadIdx.x;
+            bool won = false;
+            uint32_t v = 0;
+            if (e < e_end) {
+                v = ld_stream(col + e);
+                won = bfs_claim(level, v, depth);
+                if (won) { nf++; mf += rowptr[v + 1] - rowptr[v]; }
+            }
+            bfs_append(won, v, next_q, cnt);
+        }
+    }
+    nf = warp_sum(nf);
+    mf = warp_sum(mf);
+    if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
+}
+
+// frontier (level == cur) and visited (level != UNVIS) bitmaps from the level array
+__global__ void k_bfs_bitmaps(const int32_t *__restrict__ level, uint64_t n, int32_t cur, uint32_t *__restrict__ front,
+                              uint32_t *__restrict__ visited)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (; v < nround; v += stride) {
+        int32_t l = v < n ? level[v] : 0; // padding bits read as "visited", never in the frontier
+        unsigned f = __ballot_sync(FULL, v < n && l == cur);
+        unsigned s = __ballot_sync(FULL, l != UNVIS);
+        if (lane_id() == 0) { front[v >> 5] = f; visited[v >> 5] = s; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bfs_pull(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+           const uint64_t *__restrict__ out_rowptr, uint64_t n, const uint32_t *__restrict__ front,
+           uint32_t *__restrict__ visited, uint32_t *__restrict__ next, int32_t *__restrict__ level, int32_t depth,
+           BfsCounters *__restrict__ cnt)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nround = (n + 31) & ~31ull;
+    unsigned long long nf = 0, mf = 0, scanned = 0;
+    for (; v < nround; v += stride) {
+        const uint32_t vis = visited[v >> 5];
+        bool found = false;
+        if (vis != 0xFFFFFFFFu && !((vis >> lane_id()) & 1u) && v < n) {
+            const uint64_t a = in_rowptr[v], b = in_rowptr[v + 1];
+            if (b - a <= ROW_SPLIT) {
+                for (uint64_t e = a; e < b; e++) {
+                    const uint32_t u = in_col[e];
+                    scanned++;
+                    if ((front[u >> 5] >> (u & 31u)) & 1u) { found = true; break; }
+                }
+            }
+            if (found) { level[v] = depth; nf++; mf += out_rowptr[v + 1] - out_rowptr[v]; }
+        }
+        const unsigned fm = __ballot_sync(FULL, found);
+        if (lane_id() == 0) { next[v >> 5] = fm; if (fm) visited[v >> 5] = vis | fm; }
+    }
+    nf = warp_sum(nf);
+    mf = warp_sum(mf);
+    scanned = warp_sum(scanned);
+    if (lane_id() == 0 && (nf | scanned)) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); atomicAdd(&cnt->next_count, scanned); }
+}
+
+// rows the thread-per-vertex kernel skipped: one warp per long row, ballot early exit
+__global__ void __launch_bounds__(256)
+k_bfs_pull_long(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+                const uint64_t *__restrict__ out_rowptr, const uint32_t *__restrict__ long_rows, uint64_t n_long,
+                const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+                int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
+{
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (; wid < n_long; wid += nw) {
+        const uint32_t v = long_rows[wid];
+        if ((visited[v >> 5] >> (v & 31u)) & 1u) continue;
+        const uint64_t a = in_rowptr[v], b = in_rowptr[v + 1];
+        bool found = false;
+        unsigned long long scanned = 0;
+        for (uint64_t base = a; base < b && !found; base += 32) {
+            const uint64_t e = base + lane_id();
+            bool hit = false;
+            if (e < b) { const uint32_t u = in_col[e]; hit = (front[u >> 5] >> (u & 31u)) & 1u; }
+            found = __any_sync(FULL, hit);
+            scanned += (b - base < 32) ? (b - base) : 32;
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&cnt->next_count, scanned);
+            if (found) {
+                level[v] = depth;
+                atomicOr(&next[v >> 5], 1u << (v & 31u));
+                atomicOr(&visited[v >> 5], 1u << (v & 31u));
+                atomicAdd(&cnt->nf, 1ull);
+                atomicAdd(&cnt->mf, (unsigned long long)(out_rowptr[v + 1] - out_rowptr[v]));
+            }
+        }
+    }
+}
+
+// queue of the vertices with level == cur (pull -> push switch)
+__global__ void k_bfs_level_to_queue(const int32_t *__restrict__ level, uint64_t n, int32_t cur,
+                                     uint32_t *__restrict__ queue, BfsCounters *__restrict__ cnt)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (; v < nround; v += stride) {
+        bool in = v < n && level[v] == cur;
+        bfs_append(in, (uint32_t)v, queue, cnt);
+    }
+}
+
+__global__ void k_bfs_widen(const int32_t *__restrict__ level, uint64_t n, int64_t *__restrict__ out)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) { int32_t l = level[v]; out[v] = l == UNVIS ? GX_UNREACHED_LEVEL : (int64_t)l; }
+}
+
+} // namespace gx
+
+using namespace gx;
+
+extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(g != nullptr, "graph is NULL");
+        GX_REQUIRE(src < g->n, "source vertex out of range");
+        Context &c = ctx();
+        c.timing = gx_timing{};
+        const uint64_t n = g->n, m = g->m;
+        ensure_in_adj(g);
+        Adj &in = g->in_adj();
+        {
+            PhaseTimer tb(&c.timing.build_ms);
+            ensure_plan(in, n);
+        }
+        const uint64_t words = (n + 31) / 32;
+        g->res_i64.alloc(n);
+        DevBuf<int32_t> level(n);
+        DevBuf<uint32_t> q0(n), q1(n), bm_front(words), bm_next(words), bm_vis(words);
+        const uint64_t big_cap = m / CHUNK + m / PUSH_BIG + 16;
+        DevBuf<uint32_t> big_row(big_cap);
+        DevBuf<uint64_t> big_begin(big_cap);
+        DevBuf<BfsCounters> cnt(1);
+        uint64_t m_reach = 0, inspected = 0;
+        uint32_t levels = 0;
+        {
+            PhaseTimer tk(&c.timing.kernel_ms);
+            level.fill_byte(0xFF);
+            GX_LAUNCH(k_bfs_seed, 1, 1, 0, level.p, q0.p, (uint32_t)src);
+            uint64_t deg_src = 0;
+            {
+                uint64_t rp[2];
+                read_back(rp, g->out.rowptr.p + src, sizeof(rp));
+                deg_src = rp[1] - rp[0];
+            }
+            uint64_t nf = 1, mf = deg_src, m_unvisited = m, prev_nf = 0;
+            m_reach = deg_src;
+            bool pull = false, have_queue = true, have_bitmaps = false;
+            uint32_t *queue = q0.p, *next_q = q1.p;
+            uint32_t *front = bm_front.p, *next = bm_next.p;
+            int32_t depth = 0;
+            while (nf > 0) {
+                depth++;
+                m_unvisited = m_unvisited > mf ? m_unvisited - mf : 0;
+                // direction rule (Beamer; LAGraph uses alpha = 8, beta = 500 on the same quantities)
+                if (!pull) { if (mf > m_unvisited / 8 && nf > prev_nf && nf > 1) pull = true; }
+                else if (nf < n / 500 + 1 && nf < prev_nf) pull = false;
+                prev_nf = nf;
+                cnt.zero();
+                if (!pull) {
+                    if (!have_queue) {
+                        GX_LAUNCH(k_bfs_level_to_queue, grid_persistent(8), 256, 0, level.p, n, depth - 1, queue, cnt.p);
+                        cnt.zero(); // next_count was used as the append cursor
+                    }
+                    GX_LAUNCH(k_bfs_push, grid_for(nf * 32, 256), 256, 0, g->out.rowptr.p, g->out.col.p, queue, nf, level.p,
+                              depth, next_q, big_row.p, big_begin.p, cnt.p);
+                    GX_LAUNCH(k_bfs_push_big, grid_persistent(4), 256, 0, g->out.rowptr.p, g->out.col.p, big_row.p,
+                              big_begin.p, level.p, depth, next_q, cnt.p);
+                    uint32_t *t = queue; queue = next_q; next_q = t;
+                    have_queue = true;
+                    have_bitmaps = false;
+                    inspected += mf;
+                } else {
+                    if (!have_bitmaps) GX_LAUNCH(k_bfs_bitmaps, grid_persistent(8), 256, 0, level.p, n, depth - 1, front, bm_vis.p);
+                    GX_LAUNCH(k_bfs_pull, grid_persistent(8), 256, 0, in.rowptr.p, in.col.p, g->out.rowptr.p, n, front, bm_vis.p,
+                              next, level.p, depth, cnt.p);
+                    if (in.plan.n_long)
+                        GX_LAUNCH(k_bfs_pull_long, grid_for(in.plan.n_long * 32, 256), 256, 0, in.rowptr.p, in.col.p,
+                                  g->out.rowptr.p, in.plan.long_rows.p, in.plan.n_long, front, bm_vis.p, next, level.p, depth,
+                                  cnt.p);
+                    uint32_t *t = front; front = next; next = t;
+                    have_bitmaps = true;
+                    have_queue = false;
+                }
+                BfsCounters h;
+                read_back(&h, cnt.p, sizeof(h));
+                if (pull) inspected += h.next_count;
+                nf = h.nf;
+                mf = h.mf;
+                m_reach += mf;
+                levels++;
+            }
+            GX_LAUNCH(k_bfs_widen, grid_persistent(8), 256, 0, level.p, n, g->res_i64.p);
+        }
+        c.timing.iterations = levels;
+        c.timing.edges_inspected = inspected;
+        c.timing.algorithmic_bytes = 4 * m_reach + 8 * (n + 1) + 4 * n + 2 * (n / 8) * (uint64_t)levels;
+        if (level_host) {
+            PhaseTimer td(&c.timing.d2h_ms);
+            GX_CUDA(cudaMemcpyAsync(level_host, g->res_i64.p, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+        }
+        GX_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}

@@ -1,0 +1,194 @@
+// algo_sssp.cu -- single-source shortest paths as min.plus relaxation over
+// FP64 weights.  Replaces LA_SSSP (sssp.cpp:53-81): zero diagonal +
+// LAGr_SingleSourceShortestPath(&d, G, src, delta = 2.5).  The bucket width
+// only schedules work; the result is the fix-point d(v) = min_u fl(d(u)+w(u,v)),
+// d(src) = 0, which is unique because rounded addition is monotone -- so the
+// distances are bit-identical to LAGraph's (and to Dijkstra's).  The zero
+// diagonal the wrapper inserts (sssp.cpp:60-62) never changes a minimum and is
+// not materialised.  Unreached vertices stay +inf (printed `infinity`).
+//
+// Non-negative doubles order like their bit patterns, so relaxations are
+// atomicMin on the uint64 image of the distance.  With weights in (0,1] and
+// delta = 2.5 nearly every vertex falls in LAGraph's first bucket, i.e. the
+// reference also runs frontier sweeps of min.plus until nothing changes.
+//   k_sssp_relax      warp per frontier vertex (push over out-edges + weights);
+//                     hubs are re-queued as CHUNK-entry pieces for whole CTAs;
+//                     an improved vertex enters the next frontier once (flag)
+//   k_sssp_relax_big  CTA per piece
+// Algorithmic bytes (one-pass bound): 12m + 8(n+1) + 16n.
+#include "graph.cuh"
+
+namespace gx {
+
+constexpr uint32_t SSSP_BIG = 4096;
+constexpr unsigned long long INF_BITS = 0x7FF0000000000000ull;
+
+struct SsspCounters { unsigned long long next_count, big_count, relaxed; };
+
+__global__ void k_sssp_init(unsigned long long *__restrict__ dist, uint64_t n, uint32_t src, uint32_t *__restrict__ queue,
+                            uint32_t *__restrict__ inq)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) { dist[v] = (v == src) ? 0ull : INF_BITS; inq[v] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) queue[0] = src;
+}
+
+// relax one edge; returns true when this thread must append v to the next frontier
+__device__ __forceinline__ bool sssp_relax_edge(unsigned long long *dist, uint32_t *inq, uint32_t v, double nd)
+{
+    const unsigned long long nb = (unsigned long long)__double_as_longlong(nd);
+    if (nb >= dist[v]) return false;
+    const unsigned long long old = atomicMin(&dist[v], nb);
+    if (nb >= old) return false;
+    return atomicExch(&inq[v], 1u) == 0u;
+}
+
+__device__ __forceinline__ void sssp_append(bool won, uint32_t v, uint32_t *next_q, SsspCounters *cnt)
+{
+    const unsigned mask = __ballot_sync(FULL, won);
+    if (mask == 0) return;
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(&cnt->next_count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(FULL, base, 0);
+    if (won) next_q[base + __popc(mask & ((1u << lane_id()) - 1u))] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_sssp_relax(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const double *__restrict__ w,
+             const uint32_t *__restrict__ queue, uint64_t qn, unsigned long long *__restrict__ dist,
+             uint32_t *__restrict__ inq, uint32_t *__restrict__ next_q, uint32_t *__restrict__ big_row,
+             uint64_t *__restrict__ big_begin, SsspCounters *__restrict__ cnt)
+{
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long relaxed = 0;
+    for (; wid < qn; wid += nw) {
+        const uint32_t u = queue[wid];
+        const uint64_t a = rowptr[u], b = rowptr[u + 1];
+        if (b - a > SSSP_BIG) {
+            const uint64_t nch = (b - a + CHUNK - 1) / CHUNK;
+            unsigned long long pos = 0;
+            if (lane_id() == 0) pos = atomicAdd(&cnt->big_count, (unsigned long long)nch);
+            pos = __shfl_sync(FULL, pos, 0);
+            for (uint64_t k = lane_id(); k < nch; k += 32) { big_row[pos + k] = u; big_begin[pos + k] = a + k * CHUNK; }
+            continue;
+        }
+        const double du = __longlong_as_double((long long)dist[u]);
+        for (uint64_t base = a; base < b; base += 32) {
+            const uint64_t e = base + lane_id();
+            bool won = false;
+            uint32_t v = 0;
+            if (e < b) {
+                v = ld_stream(col + e);
+                won = sssp_relax_edge(dist, inq, v, du + ld_stream_f64(w + e));
+                relaxed++;
+            }
+            sssp_append(won, v, next_q, cnt);
+        }
+    }
+    relaxed = warp_sum(relaxed);
+    if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
+}
+
+__global__ void __launch_bounds__(256)
+k_sssp_relax_big(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const double *__restrict__ w,
+                 const uint32_t *__restrict__ big_row, const uint64_t *__restrict__ big_begin,
+                 unsigned long long *__restrict__ dist, uint32_t *__restrict__ inq, uint32_t *__restrict__ next_q,
+                 SsspCounters *__restrict__ cnt)
+{
+    const unsigned long long nbig = cnt->big_count;
+    unsigned long long relaxed = 0;
+    for (unsigned long long c = blockIdx.x; c < nbig; c += gridDim.x) {
+        const uint32_t u = big_row[c];
+        const uint64_t b0 = big_begin[c];
+        const uint64_t row_end = rowptr[u + 1];
+        const uint64_t e_end = (b0 + CHUNK < row_end) ? b0 + CHUNK : row_end;
+        const double du = __longlong_as_double((long long)dist[u]);
+        for (uint64_t base = b0; base < e_end; base += 256) {
+            const uint64_t e = base + threadIdx.x;
+            bool won = false;
+            uint32_t v = 0;
+            if (e < e_end) {
+                v = ld_stream(col + e);
+                won = sssp_relax_edge(dist, inq, v, du + ld_stream_f64(w + e));
+                relaxed++;
+            }
+            sssp_append(won, v, next_q, cnt);
+        }
+    }
+    relaxed = warp_sum(relaxed);
+    if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
+}
+
+// Frontier members drop their "queued" flag in a kernel of their own, BEFORE the relax kernels:
+// any improvement of u that lands while u is being expanded (possibly from a distance read a
+// moment too early) then finds the flag clear and re-queues u for the next round.
+__global__ void k_sssp_clear(const uint32_t *__restrict__ queue, uint64_t qn, uint32_t *__restrict__ inq)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < qn; i += stride) inq[queue[i]] = 0;
+}
+
+__global__ void k_sssp_out(const unsigned long long *__restrict__ dist, uint64_t n, double *__restrict__ out)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) out[v] = __longlong_as_double((long long)dist[v]);
+}
+
+} // namespace gx
+
+using namespace gx;
+
+extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(g != nullptr, "graph is NULL");
+        GX_REQUIRE(src < g->n, "source vertex out of range");
+        GX_REQUIRE(g->weighted, "SSSP needs a weighted graph (graph.mtx of type real / GrB_FP64)");
+        Context &c = ctx();
+        c.timing = gx_timing{};
+        const uint64_t n = g->n, m = g->m;
+        g->res_f64.alloc(n);
+        DevBuf<unsigned long long> dist(n);
+        DevBuf<uint32_t> inq(n), q0(n), q1(n);
+        const uint64_t big_cap = m / CHUNK + m / SSSP_BIG + 16;
+        DevBuf<uint32_t> big_row(big_cap);
+        DevBuf<uint64_t> big_begin(big_cap);
+        DevBuf<SsspCounters> cnt(1);
+        uint64_t relaxed = 0;
+        uint32_t rounds = 0;
+        {
+            PhaseTimer tk(&c.timing.kernel_ms);
+            GX_LAUNCH(k_sssp_init, grid_persistent(8), 256, 0, dist.p, n, (uint32_t)src, q0.p, inq.p);
+            uint32_t *queue = q0.p, *next_q = q1.p;
+            uint64_t qn = 1;
+            while (qn) {
+                cnt.zero();
+                GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, inq.p);
+                GX_LAUNCH(k_sssp_relax, grid_for(qn * 32, 256), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue, qn,
+                          dist.p, inq.p, next_q, big_row.p, big_begin.p, cnt.p);
+                GX_LAUNCH(k_sssp_relax_big, grid_persistent(4), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, big_row.p,
+                          big_begin.p, dist.p, inq.p, next_q, cnt.p);
+                SsspCounters h;
+                read_back(&h, cnt.p, sizeof(h));
+                qn = h.next_count;
+                relaxed += h.relaxed;
+                uint32_t *t = queue; queue = next_q; next_q = t;
+                rounds++;
+            }
+            GX_LAUNCH(k_sssp_out, grid_persistent(8), 256, 0, dist.p, n, g->res_f64.p);
+        }
+        c.timing.iterations = rounds;
+        c.timing.edges_inspected = relaxed;
+        c.timing.algorithmic_bytes = 12 * m + 8 * (n + 1) + 16 * n;
+        if (dist_host) {
+            PhaseTimer td(&c.timing.d2h_ms);
+            GX_CUDA(cudaMemcpyAsync(dist_host, g->res_f64.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        }
+        GX_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}

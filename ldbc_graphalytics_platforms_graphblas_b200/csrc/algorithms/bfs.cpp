@@ -1,0 +1,47 @@
+// bfs -- per-algorithm binary `bin/exe/bfs` (execute-job.sh:70-79).  Same flags, log lines,
+// exit codes and output format as the reference wrapper (src/algorithms/bfs.cpp:86-113);
+// the LAGraph call is replaced by gx_bfs on the B200.
+#include <algorithm>
+#include <iostream>
+
+#include "cli_common.h"
+
+void SerializeBFSResult(const std::vector<int64_t> &level, const std::vector<GrB_Index> &mapping,
+                        const BenchmarkParameters &parameters)
+{
+    ResultWriter file = OpenOutput(parameters);
+    // unreachable vertices carry GX_UNREACHED_LEVEL == 9223372036854775807 (bfs.cpp:59-63)
+    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_int(mapping[v], level[v]);
+}
+
+std::vector<int64_t> LA_BFS(gx_graph *G, GrB_Index sourceVertex, GrB_Index n)
+{
+    ComputationTimer timer{"BFS"};
+    std::vector<int64_t> level(n);
+    OK(gx_bfs(G, sourceVertex, level.data()));
+    return level;
+}
+
+int main(int argc, char **argv)
+{
+    BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
+    InitDevice();
+    HostMatrix A = ReadMatrixMarket(parameters);
+    std::vector<GrB_Index> mapping = ReadMapping(parameters);
+
+    auto it = std::find(mapping.begin(), mapping.end(), (GrB_Index)parameters.source_vertex);
+    if (it == mapping.end()) {
+        std::cout << "Source vertex not found in mapping" << std::endl;
+        return -1;
+    }
+    const GrB_Index sourceVertex = (GrB_Index)std::distance(mapping.begin(), it);
+
+    gx_graph *G = UploadGraph(A, parameters.directed, GX_CACHE_AT);
+    std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
+    std::vector<int64_t> result = LA_BFS(G, sourceVertex, A.nrows);
+    std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
+
+    SerializeBFSResult(result, mapping, parameters);
+    OK(gx_graph_free(G));
+    return 0;
+}

@@ -1,0 +1,39 @@
+// lcc -- per-algorithm binary `bin/exe/lcc` (execute-job.sh:117-126), the drop-in for
+// src/algorithms/lcc.cpp:73-90 with LAGraph_lcc replaced by gx_lcc.  The reference times all
+// of LAGraph_lcc, including building A v A' (lcc.cpp:82-84); so does this one.
+#include <iostream>
+
+#include "cli_common.h"
+
+void SerializeLCCResult(const std::vector<double> &lcc, const std::vector<GrB_Index> &mapping,
+                        const BenchmarkParameters &parameters)
+{
+    ResultWriter file = OpenOutput(parameters);
+    // vertices LAGraph leaves without an entry are written as 0.0 (lcc.cpp:49-54); gx_lcc returns 0.0 for them
+    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_sci(mapping[v], lcc[v]);
+}
+
+std::vector<double> LA_LCC(gx_graph *G, GrB_Index n)
+{
+    ComputationTimer timer{"LCC"};
+    std::vector<double> lcc(n);
+    OK(gx_lcc(G, lcc.data()));
+    return lcc;
+}
+
+int main(int argc, char **argv)
+{
+    BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
+    InitDevice();
+    HostMatrix A = ReadMatrixMarket(parameters);
+    std::vector<GrB_Index> mapping = ReadMapping(parameters);
+
+    gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
+    std::vector<double> result = LA_LCC(G, A.nrows);
+    std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
+
+    SerializeLCCResult(result, mapping, parameters);
+    OK(gx_graph_free(G));
+    return 0;
+}

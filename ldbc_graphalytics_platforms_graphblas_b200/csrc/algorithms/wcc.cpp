@@ -1,0 +1,39 @@
+// wcc -- per-algorithm binary `bin/exe/wcc` (execute-job.sh:81-90), the drop-in for
+// src/algorithms/wcc.cpp:68-85 with A v A' + LAGr_ConnectedComponents replaced by gx_wcc.
+#include <iostream>
+
+#include "cli_common.h"
+
+void SerializeWCCResult(const std::vector<uint64_t> &comp, const std::vector<GrB_Index> &mapping,
+                        const BenchmarkParameters &parameters)
+{
+    ResultWriter file = OpenOutput(parameters);
+    // like the reference, the component id is the dense representative, not mapped back
+    // (wcc.cpp:31-34); the validator only needs equivalent partitions
+    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_uint(mapping[v], comp[v]);
+}
+
+std::vector<uint64_t> WeaklyConnectedComponents(gx_graph *G, GrB_Index n)
+{
+    ComputationTimer total_timer{"WeaklyConnectedComponents"};
+    std::vector<uint64_t> comp(n);
+    OK(gx_wcc(G, comp.data()));
+    return comp;
+}
+
+int main(int argc, char **argv)
+{
+    BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
+    InitDevice();
+    HostMatrix A = ReadMatrixMarket(parameters);
+    std::vector<GrB_Index> mapping = ReadMapping(parameters);
+
+    gx_graph *G = UploadGraph(A, parameters.directed, GX_CACHE_AT);
+    std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
+    std::vector<uint64_t> result = WeaklyConnectedComponents(G, A.nrows);
+    std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
+
+    SerializeWCCResult(result, mapping, parameters);
+    OK(gx_graph_free(G));
+    return 0;
+}

@@ -1,0 +1,546 @@
+// graph.cu -- host CSR -> device graph, transposition (LAGraph_Cached_AT
+// analogue), LCC union/orientation cache.  Replaces GxB_Matrix_export_CSR + the
+// cudaMalloc/cudaMemcpy block of the reference's cdlp_gpu
+// (cdlp_cuda.cu:181, cdlp_kernel.cu:1162-1196).
+//
+// Construction-time sorting / compaction uses CUB device primitives (CUDA
+// toolkit headers); the per-algorithm hot loops in algo_*.cu are hand-written.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <vector>
+
+#include "graph.cuh"
+
+namespace gx {
+
+int bits_for(uint64_t n)
+{
+    int b = 1;
+    while (b < 64 && (1ull << b) < n) b++;
+    return b;
+}
+
+// ------------------------------------------------------------------------- small kernels
+__global__ void k_narrow_u64(const uint64_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t count,
+                             uint64_t n, int *__restrict__ bad)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        uint64_t v = in[i];
+        if (v >= n) *bad = 1;
+        out[i] = (uint32_t)v;
+    }
+}
+
+__global__ void k_validate(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n,
+                           uint64_t m, int *__restrict__ bad, int *__restrict__ unsorted)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = i; v < n; v += stride) {
+        uint64_t a = rowptr[v], b = rowptr[v + 1];
+        if (a > b || b > m) { *bad = 1; continue; }
+        if (v == 0 && a != 0) *bad = 1;
+        if (v == n - 1 && b != m) *bad = 1;
+    }
+    for (uint64_t e = i; e < m; e += stride)
+        if (col[e] >= n) *bad = 1;
+    // sortedness: entry e and e+1 in the same row must be non-decreasing.  Row membership of
+    // e+1 is checked in k_check_sorted (needs row ids); here only the cheap global hint.
+    (void)unsorted;
+}
+
+// one thread per row: is the row sorted (non-decreasing)?
+__global__ void k_check_sorted(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n,
+                               int *__restrict__ unsorted)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) {
+        uint64_t a = rowptr[v], b = rowptr[v + 1];
+        for (uint64_t e = a + 1; e < b; e++)
+            if (col[e] < col[e - 1]) { *unsorted = 1; break; }
+    }
+}
+
+// row id of every entry: binary search of the entry offset in rowptr (balanced
+// under degree skew, no per-row loops).
+__global__ void k_expand_rows(const uint64_t *__restrict__ rowptr, uint64_t n, uint64_t m,
+                              uint32_t *__restrict__ row_of_edge)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) {
+        uint64_t lo = 0, hi = n; // find largest r with rowptr[r] <= e
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= e) lo = mid; else hi = mid;
+        }
+        row_of_edge[e] = (uint32_t)lo;
+    }
+}
+
+template <class K, int SHIFT>
+__global__ void k_rowptr_from_sorted(const K *__restrict__ keys, uint64_t m, uint64_t n, uint64_t *__restrict__ rowptr)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v <= n; v += stride) {
+        uint64_t lo = 0, hi = m; // first position with (key >> SHIFT) >= v
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if ((uint64_t)(keys[mid] >> SHIFT) < v) lo = mid + 1; else hi = mid;
+        }
+        rowptr[v] = lo;
+    }
+}
+
+void expand_row_ids(const uint64_t *rowptr, uint64_t n, uint64_t m, uint32_t *row_of_edge)
+{
+    if (!m) return;
+    GX_LAUNCH(k_expand_rows, grid_for(m, 256, 4), 256, 0, rowptr, n, m, row_of_edge);
+}
+
+void rowptr_from_sorted_rows(const uint32_t *sorted_rows, uint64_t m, uint64_t n, uint64_t *rowptr)
+{
+    GX_LAUNCH((k_rowptr_from_sorted<uint32_t, 0>), grid_for(n + 1, 256), 256, 0, sorted_rows, m, n, rowptr);
+}
+
+void rowptr_from_sorted_keys(const uint64_t *sorted_keys, uint64_t m, uint64_t n, uint64_t *rowptr)
+{
+    GX_LAUNCH((k_rowptr_from_sorted<uint64_t, 32>), grid_for(n + 1, 256), 256, 0, sorted_keys, m, n, rowptr);
+}
+
+void sort_keys64(DevBuf<uint64_t> &keys, uint64_t count, int end_bit)
+{
+    if (count < 2) return;
+    DevBuf<uint64_t> alt(count);
+    cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t)count, 0, end_bit, ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t)count, 0, end_bit, ctx().stream));
+    if (db.Current() != keys.p) std::swap(keys.p, alt.p); // sizes are equal; alt frees the other buffer
+}
+
+void sort_pairs64_f64(DevBuf<uint64_t> &keys, DevBuf<double> &vals, uint64_t count, int end_bit)
+{
+    if (count < 2) return;
+    DevBuf<uint64_t> kalt(count);
+    DevBuf<double> valt(count);
+    cub::DoubleBuffer<uint64_t> dk(keys.p, kalt.p);
+    cub::DoubleBuffer<double> dv(vals.p, valt.p);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t)count, 0, end_bit, ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t)count, 0, end_bit, ctx().stream));
+    if (dk.Current() != keys.p) std::swap(keys.p, kalt.p);
+    if (dv.Current() != vals.p) std::swap(vals.p, valt.p);
+}
+
+// ------------------------------------------------------------------------- upload + finish
+__global__ void k_make_keys(const uint32_t *__restrict__ row, const uint32_t *__restrict__ col, uint64_t m,
+                            uint64_t *__restrict__ keys)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) keys[e] = ((uint64_t)row[e] << 32) | col[e];
+}
+
+__global__ void k_low32(const uint64_t *__restrict__ keys, uint64_t m, uint32_t *__restrict__ out)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) out[e] = (uint32_t)keys[e];
+}
+
+__global__ void k_high32(const uint64_t *__restrict__ keys, uint64_t m, uint32_t *__restrict__ out)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) out[e] = (uint32_t)(keys[e] >> 32);
+}
+
+static int read_flag(const int *dflag)
+{
+    int h = 0;
+    read_back(&h, dflag, sizeof(int));
+    return h;
+}
+
+void finish_graph(gx_graph *g)
+{
+    if (g->n == 0) return;
+    DevBuf<int> flags(2);
+    flags.zero();
+    GX_LAUNCH(k_validate, grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->n, g->m, flags.p, flags.p + 1);
+    GX_LAUNCH(k_check_sorted, grid_for(g->n, 256), 256, 0, g->out.rowptr.p, g->out.col.p, g->n, flags.p + 1);
+    int h[2] = {0, 0};
+    read_back(h, flags.p, sizeof(h));
+    if (h[0]) throw Error(GX_ERR_INVALID, "CSR arrays are inconsistent (rowptr not monotone or column id >= n)");
+    if (h[1] && g->m > 1) {
+        // jumbled rows (GxB export may return them so): sort (row, col) keys once
+        DevBuf<uint32_t> rows(g->m);
+        expand_row_ids(g->out.rowptr.p, g->n, g->m, rows.p);
+        DevBuf<uint64_t> keys(g->m);
+        GX_LAUNCH(k_make_keys, grid_persistent(8), 256, 0, rows.p, g->out.col.p, g->m, keys.p);
+        if (g->weighted) sort_pairs64_f64(keys, g->out.w, g->m, 32 + bits_for(g->n));
+        else sort_keys64(keys, g->m, 32 + bits_for(g->n));
+        GX_LAUNCH(k_low32, grid_persistent(8), 256, 0, keys.p, g->m, g->out.col.p);
+    }
+}
+
+static void upload_common(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t *rowptr, const double *weights,
+                          int directed)
+{
+    GX_REQUIRE(n < 0xFFFFFFFEull, "n must be < 2^32 - 2");
+    GX_REQUIRE(rowptr != nullptr || n == 0, "rowptr is NULL");
+    g->n = n;
+    g->m = nnz;
+    g->directed = directed != 0;
+    g->weighted = weights != nullptr;
+    g->out.rowptr.alloc(n + 1);
+    if (n) GX_CUDA(cudaMemcpyAsync(g->out.rowptr.p, rowptr, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx().stream));
+    else g->out.rowptr.zero();
+    g->out.col.alloc(nnz);
+    if (weights) {
+        g->out.w.alloc(nnz);
+        if (nnz) GX_CUDA(cudaMemcpyAsync(g->out.w.p, weights, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+    }
+}
+
+void ensure_in_adj(gx_graph *g)
+{
+    if (!g->directed || g->have_in) return;
+    PhaseTimer t(&ctx().timing.build_ms);
+    const uint64_t n = g->n, m = g->m;
+    g->in.rowptr.alloc(n + 1);
+    g->in.col.alloc(m);
+    if (m == 0) {
+        g->in.rowptr.zero();
+        g->have_in = true;
+        return;
+    }
+    // stable LSD radix sort of (key = column, value = row): rows stay ascending inside a column
+    DevBuf<uint32_t> keys(m), keys_alt(m), rows(m);
+    GX_CUDA(cudaMemcpyAsync(keys.p, g->out.col.p, m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx().stream));
+    expand_row_ids(g->out.rowptr.p, n, m, rows.p);
+    cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p);
+    cub::DoubleBuffer<uint32_t> dv(rows.p, g->in.col.p);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t)m, 0, bits_for(n), ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t)m, 0, bits_for(n), ctx().stream));
+    if (dv.Current() != g->in.col.p) std::swap(rows.p, g->in.col.p);
+    rowptr_from_sorted_rows(dk.Current(), m, n, g->in.rowptr.p);
+    g->have_in = true;
+}
+
+// ------------------------------------------------------------------------- LCC cache
+// key = (a << 33) | (b << 1) | rev : rev = 0 for (a,b) in A, 1 for the mirrored copy of (b,a)
+__global__ void k_lcc_keys(const uint32_t *__restrict__ row, const uint32_t *__restrict__ col, uint64_t m,
+                           int directed, uint64_t *__restrict__ keys)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) {
+        uint64_t a = row[e], b = col[e];
+        uint64_t sentinel = ~0ull;
+        if (directed) {
+            keys[2 * e] = (a == b) ? sentinel : ((a << 33) | (b << 1));
+            keys[2 * e + 1] = (a == b) ? sentinel : ((b << 33) | (a << 1) | 1ull);
+        } else {
+            keys[e] = (a == b) ? sentinel : ((a << 33) | (b << 1));
+        }
+    }
+}
+
+// group head of equal (a,b): emits (a << 32) | mult31 | b, mult31 set when both directions exist
+__global__ void k_lcc_heads(const uint64_t *__restrict__ keys, uint64_t cnt, int directed,
+                            uint64_t *__restrict__ ukeys, uint8_t *__restrict__ head)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < cnt; i += stride) {
+        uint64_t k = keys[i];
+        bool is_head = (k != ~0ull) && (i == 0 || (keys[i - 1] >> 1) != (k >> 1));
+        uint64_t out = 0;
+        if (is_head) {
+            bool fwd = (k & 1) == 0, rev = (k & 1) != 0;
+            for (uint64_t j = i + 1; j < cnt && (keys[j] >> 1) == (k >> 1); j++) {
+                if (keys[j] & 1) rev = true; else fwd = true;
+            }
+            uint64_t a = k >> 33, b = (k >> 1) & 0xFFFFFFFFull;
+            bool both = directed ? (fwd && rev) : true;
+            out = (a << 32) | (both ? (uint64_t)LCC_MULT_BIT : 0ull) | b;
+        }
+        ukeys[i] = out;
+        head[i] = is_head ? 1 : 0;
+    }
+}
+
+__global__ void k_degree_from_rowptr(const uint64_t *__restrict__ rowptr, uint64_t n, uint32_t *__restrict__ deg)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) deg[v] = (uint32_t)(rowptr[v + 1] - rowptr[v]);
+}
+
+__global__ void k_lcc_orient_flags(const uint64_t *__restrict__ ukeys, uint64_t um, const uint32_t *__restrict__ udeg,
+                                   uint8_t *__restrict__ keep)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < um; i += stride) {
+        uint64_t k = ukeys[i];
+        uint32_t a = (uint32_t)(k >> 32), b = (uint32_t)k & ~LCC_MULT_BIT;
+        uint32_t da = udeg[a], db = udeg[b];
+        keep[i] = (da < db || (da == db && a < b)) ? 1 : 0;
+    }
+}
+
+__global__ void k_lcc_list_bytes(const uint64_t *__restrict__ orowptr, const uint32_t *__restrict__ orow,
+                                 const uint32_t *__restrict__ ocol, uint64_t om, unsigned long long *__restrict__ total)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (; i < om; i += stride) {
+        uint32_t u = orow[i], v = ocol[i] & ~LCC_MULT_BIT;
+        acc += (orowptr[u + 1] - orowptr[u]) + (orowptr[v + 1] - orowptr[v]);
+    }
+    acc = warp_sum(acc);
+    if (lane_id() == 0 && acc) atomicAdd(total, acc);
+}
+
+uint64_t select_flagged(const uint64_t *in, const uint8_t *flags, uint64_t count, DevBuf<uint64_t> &out)
+{
+    DevBuf<uint64_t> nsel(1);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, in, flags, out.p, nsel.p, (int64_t)count, ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, in, flags, out.p, nsel.p, (int64_t)count, ctx().stream));
+    uint64_t h = 0;
+    read_back(&h, nsel.p, sizeof(h));
+    return h;
+}
+
+void ensure_lcc_cache(gx_graph *g)
+{
+    if (g->have_lcc) return;
+    PhaseTimer t(&ctx().timing.build_ms);
+    const uint64_t n = g->n, m = g->m;
+    GX_REQUIRE(n < 0x7FFFFFFFull, "LCC needs n < 2^31");
+    g->udeg.alloc(n);
+    g->orowptr.alloc(n + 1);
+    const uint64_t cnt = g->directed ? 2 * m : m;
+    if (cnt == 0) {
+        g->udeg.zero();
+        g->orowptr.zero();
+        g->om = 0;
+        g->have_lcc = true;
+        return;
+    }
+    DevBuf<uint64_t> ukeys_sel;
+    uint64_t um = 0;
+    {
+        DevBuf<uint64_t> keys(cnt);
+        {
+            DevBuf<uint32_t> rows(m);
+            expand_row_ids(g->out.rowptr.p, n, m, rows.p);
+            GX_LAUNCH(k_lcc_keys, grid_persistent(8), 256, 0, rows.p, g->out.col.p, m, g->directed ? 1 : 0, keys.p);
+        }
+        // an undirected store is already sorted by (row, col); a directed one needs the merge sort
+        if (g->directed) sort_keys64(keys, cnt, 64);
+        DevBuf<uint64_t> ukeys(cnt);
+        DevBuf<uint8_t> head(cnt);
+        GX_LAUNCH(k_lcc_heads, grid_persistent(8), 256, 0, keys.p, cnt, g->directed ? 1 : 0, ukeys.p, head.p);
+        keys.release();
+        ukeys_sel.alloc(cnt);
+        um = select_flagged(ukeys.p, head.p, cnt, ukeys_sel);
+    }
+    // degrees in U, then keep only low -> high (degree, id) entries
+    DevBuf<uint64_t> urowptr(n + 1);
+    rowptr_from_sorted_keys(ukeys_sel.p, um, n, urowptr.p);
+    GX_LAUNCH(k_degree_from_rowptr, grid_for(n, 256), 256, 0, urowptr.p, n, g->udeg.p);
+    DevBuf<uint8_t> keep(um ? um : 1);
+    DevBuf<uint64_t> okeys(um ? um : 1);
+    uint64_t om = 0;
+    if (um) {
+        GX_LAUNCH(k_lcc_orient_flags, grid_persistent(8), 256, 0, ukeys_sel.p, um, g->udeg.p, keep.p);
+        om = select_flagged(ukeys_sel.p, keep.p, um, okeys);
+    }
+    g->om = om;
+    g->ocol.alloc(om ? om : 1);
+    g->orow.alloc(om ? om : 1);
+    rowptr_from_sorted_keys(okeys.p, om, n, g->orowptr.p);
+    if (om) {
+        GX_LAUNCH(k_low32, grid_persistent(8), 256, 0, okeys.p, om, g->ocol.p);
+        GX_LAUNCH(k_high32, grid_persistent(8), 256, 0, okeys.p, om, g->orow.p);
+        DevBuf<unsigned long long> total(1);
+        total.zero();
+        GX_LAUNCH(k_lcc_list_bytes, grid_persistent(8), 256, 0, g->orowptr.p, g->orow.p, g->ocol.p, om, total.p);
+        unsigned long long h = 0;
+        read_back(&h, total.p, sizeof(h));
+        g->lcc_list_bytes = 4ull * h;
+    }
+    g->have_lcc = true;
+}
+
+// ------------------------------------------------------------------------- max degree vertex
+__global__ void k_max_degree(const uint64_t *__restrict__ rowptr, uint64_t n, unsigned long long *__restrict__ best)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long b = 0;
+    for (; v < n; v += stride) {
+        // (degree, ~id) packed so that max picks the largest degree, then the smallest id
+        unsigned long long d = rowptr[v + 1] - rowptr[v];
+        unsigned long long key = (d << 32) | (0xFFFFFFFFull - v);
+        b = key > b ? key : b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long x = __shfl_xor_sync(FULL, b, o);
+        b = x > b ? x : b;
+    }
+    if (lane_id() == 0) atomicMax(best, b);
+}
+
+} // namespace gx
+
+using namespace gx;
+
+void gx_cdlp_plan_free(void *p);
+gx_graph::~gx_graph()
+{
+    if (cdlp_plan) gx_cdlp_plan_free(cdlp_plan);
+}
+
+// ------------------------------------------------------------------------- C ABI
+extern "C" int gx_graph_create_csr(gx_graph **out, uint64_t n, uint64_t nnz, const uint64_t *rowptr,
+                                   const uint64_t *colidx, const double *weights, int directed)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(out != nullptr, "graph handle is NULL");
+        GX_REQUIRE(colidx != nullptr || nnz == 0, "colidx is NULL");
+        ctx().timing = gx_timing{};
+        gx_graph *g = new gx_graph();
+        try {
+            {
+                PhaseTimer t(&ctx().timing.h2d_ms);
+                upload_common(g, n, nnz, rowptr, weights, directed);
+                // GrB_Index (uint64) column ids: staged in chunks and narrowed to 4 bytes on the device
+                const uint64_t CH = 1ull << 26;
+                DevBuf<uint64_t> stage(nnz < CH ? nnz : CH);
+                DevBuf<int> bad(1);
+                bad.zero();
+                for (uint64_t o = 0; o < nnz; o += CH) {
+                    uint64_t c = nnz - o < CH ? nnz - o : CH;
+                    GX_CUDA(cudaMemcpyAsync(stage.p, colidx + o, c * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx().stream));
+                    GX_LAUNCH(k_narrow_u64, grid_persistent(8), 256, 0, stage.p, g->out.col.p + o, c, n, bad.p);
+                }
+                if (nnz && read_flag(bad.p)) throw Error(GX_ERR_INVALID, "column id >= n");
+            }
+            {
+                PhaseTimer t(&ctx().timing.build_ms);
+                finish_graph(g);
+            }
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        *out = g;
+    });
+}
+
+extern "C" int gx_graph_create_csr32(gx_graph **out, uint64_t n, uint64_t nnz, const uint64_t *rowptr,
+                                     const uint32_t *colidx, const double *weights, int directed)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(out != nullptr, "graph handle is NULL");
+        GX_REQUIRE(colidx != nullptr || nnz == 0, "colidx is NULL");
+        ctx().timing = gx_timing{};
+        gx_graph *g = new gx_graph();
+        try {
+            {
+                PhaseTimer t(&ctx().timing.h2d_ms);
+                upload_common(g, n, nnz, rowptr, weights, directed);
+                if (nnz) GX_CUDA(cudaMemcpyAsync(g->out.col.p, colidx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx().stream));
+            }
+            {
+                PhaseTimer t(&ctx().timing.build_ms);
+                finish_graph(g);
+            }
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        *out = g;
+    });
+}
+
+extern "C" int gx_graph_free(gx_graph *g)
+{
+    return guarded([&] {
+        if (!g) return;
+        delete g;
+        if (ctx().ready) GX_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+extern "C" int gx_graph_info(const gx_graph *g, uint64_t *n, uint64_t *nnz, int *directed, int *weighted)
+{
+    return guarded([&] {
+        GX_REQUIRE(g != nullptr, "graph is NULL");
+        if (n) *n = g->n;
+        if (nnz) *nnz = g->m;
+        if (directed) *directed = g->directed;
+        if (weighted) *weighted = g->weighted;
+    });
+}
+
+extern "C" int gx_graph_cache(gx_graph *g, unsigned what)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(g != nullptr, "graph is NULL");
+        ctx().timing = gx_timing{};
+        if (what & GX_CACHE_AT) ensure_in_adj(g);
+        if (what & GX_CACHE_LCC) ensure_lcc_cache(g);
+        GX_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+extern "C" int gx_graph_download(const gx_graph *g, uint64_t *rowptr, uint32_t *colidx, double *weights)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(g != nullptr, "graph is NULL");
+        cudaStream_t s = ctx().stream;
+        if (rowptr) GX_CUDA(cudaMemcpyAsync(rowptr, g->out.rowptr.p, (g->n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        if (colidx && g->m) GX_CUDA(cudaMemcpyAsync(colidx, g->out.col.p, g->m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (weights && g->weighted && g->m)
+            GX_CUDA(cudaMemcpyAsync(weights, g->out.w.p, g->m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        GX_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+extern "C" int gx_graph_max_degree_vertex(const gx_graph *g, uint64_t *v)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(g != nullptr && v != nullptr, "NULL argument");
+        GX_REQUIRE(g->n > 0, "empty graph");
+        DevBuf<unsigned long long> best(1);
+        best.zero();
+        GX_LAUNCH(k_max_degree, grid_persistent(4), 256, 0, g->out.rowptr.p, g->n, best.p);
+        unsigned long long h = 0;
+        read_back(&h, best.p, sizeof(h));
+        *v = 0xFFFFFFFFull - (h & 0xFFFFFFFFull);
+    });
+}

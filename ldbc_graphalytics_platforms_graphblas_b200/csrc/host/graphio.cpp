@@ -1,0 +1,350 @@
+#include "graphio.h"
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+
+#include "computation_timer.hpp"
+
+namespace {
+
+constexpr size_t GRB_HEADER_LEN = 512; // LAGRAPH_BIN_HEADER
+
+struct FileBytes {
+    std::vector<char> data;
+    explicit FileBytes(const std::string &path)
+    {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("Cannot open file: " + path);
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        data.resize((size_t)sz + 1);
+        if (sz && fread(data.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); throw std::runtime_error("Short read: " + path); }
+        data[(size_t)sz] = '\0';
+        fclose(f);
+    }
+};
+
+inline const char *skip_ws(const char *p) { while (*p == ' ' || *p == '\t' || *p == '\r') p++; return p; }
+inline const char *next_line(const char *p) { while (*p && *p != '\n') p++; return *p ? p + 1 : p; }
+
+inline uint64_t parse_u64(const char *&p)
+{
+    p = skip_ws(p);
+    uint64_t v = 0;
+    if (*p < '0' || *p > '9') throw std::runtime_error("Matrix Market file: expected an integer");
+    while (*p >= '0' && *p <= '9') v = v * 10 + (uint64_t)(*p++ - '0');
+    return v;
+}
+
+// COO (0-based, already mirrored for symmetric files) -> CSR with sorted, duplicate-free rows.
+// Self-loops are dropped and duplicates keep the smallest weight: the algorithms assume a
+// loop-free simple graph (LAGraph_cdlp.c: "assume ... no self edges").
+HostMatrix coo_to_csr(GrB_Index n, std::vector<uint32_t> &src, std::vector<uint32_t> &dst, std::vector<double> &val, bool weighted)
+{
+    HostMatrix A;
+    A.nrows = n;
+    A.iso = !weighted;
+    const size_t nz = src.size();
+    std::vector<GrB_Index> cnt(n + 1, 0);
+    for (size_t k = 0; k < nz; k++)
+        if (src[k] != dst[k]) cnt[src[k] + 1]++;
+    for (GrB_Index i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    std::vector<uint32_t> col(cnt[n]);
+    std::vector<double> w(weighted ? cnt[n] : 0);
+    {
+        std::vector<GrB_Index> cur(cnt.begin(), cnt.end() - 1);
+        for (size_t k = 0; k < nz; k++) {
+            if (src[k] == dst[k]) continue;
+            GrB_Index p = cur[src[k]]++;
+            col[p] = dst[k];
+            if (weighted) w[p] = val[k];
+        }
+    }
+    A.Ap.assign(n + 1, 0);
+    A.Aj.reserve(col.size());
+    if (weighted) A.Ax.reserve(col.size());
+    std::vector<uint32_t> perm;
+    for (GrB_Index i = 0; i < n; i++) {
+        const GrB_Index a = cnt[i], b = cnt[i + 1];
+        if (weighted) {
+            perm.resize(b - a);
+            std::iota(perm.begin(), perm.end(), 0u);
+            std::sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) {
+                return col[a + x] != col[a + y] ? col[a + x] < col[a + y] : w[a + x] < w[a + y];
+            });
+            for (size_t k = 0; k < perm.size(); k++) {
+                const uint32_t c = col[a + perm[k]];
+                if (k && c == A.Aj.back() && A.Aj.size() > A.Ap[i]) continue;
+                A.Aj.push_back(c);
+                A.Ax.push_back(w[a + perm[k]]);
+            }
+        } else {
+            std::sort(col.begin() + a, col.begin() + b);
+            for (GrB_Index k = a; k < b; k++) {
+                if (k > a && col[k] == col[k - 1]) continue;
+                A.Aj.push_back(col[k]);
+            }
+        }
+        A.Ap[i + 1] = A.Aj.size();
+    }
+    A.nvals = A.Aj.size();
+    return A;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------- .mtx
+// Format as written by bin/py/relabel.py:64-79: banner `%%MatrixMarket matrix coordinate
+// integer|real general|symmetric`, `%%GraphBLAS GrB_BOOL|GrB_FP64`, `n n nnz`, then 1-based
+// `src dst val` in no particular order.  Symmetric files list each edge once in either
+// triangle; every off-diagonal entry is mirrored (what LAGraph_MMRead does).
+HostMatrix ReadMtxFile(const std::string &path)
+{
+    FileBytes file(path);
+    const char *p = file.data.data();
+    if (std::strncmp(p, "%%MatrixMarket", 14) != 0) throw std::runtime_error("Not a Matrix Market file: " + path);
+    std::string banner(p, next_line(p) - p);
+    std::transform(banner.begin(), banner.end(), banner.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (banner.find("coordinate") == std::string::npos) throw std::runtime_error("Only coordinate Matrix Market files are supported");
+    const bool symmetric = banner.find("symmetric") != std::string::npos;
+    const bool pattern = banner.find("pattern") != std::string::npos;
+    const bool weighted = banner.find("real") != std::string::npos || banner.find("double") != std::string::npos;
+    p = next_line(p);
+    while (*p == '%') p = next_line(p);
+    const GrB_Index nrows = parse_u64(p), ncols = parse_u64(p), nnz = parse_u64(p);
+    if (nrows != ncols) throw std::runtime_error("Adjacency matrix must be square");
+    if (nrows >= 0xFFFFFFFEull) throw std::runtime_error("More than 2^32 - 2 vertices are not supported");
+    p = next_line(p);
+    std::vector<uint32_t> src, dst;
+    std::vector<double> val;
+    const size_t cap = symmetric ? 2 * nnz : nnz;
+    src.reserve(cap);
+    dst.reserve(cap);
+    if (weighted) val.reserve(cap);
+    for (GrB_Index k = 0; k < nnz; k++) {
+        while (*p == '\n' || *p == '\r' || *p == ' ') p++;
+        if (!*p) throw std::runtime_error("Matrix Market file ends before nnz entries were read");
+        const GrB_Index i = parse_u64(p), j = parse_u64(p);
+        if (i < 1 || j < 1 || i > nrows || j > nrows) throw std::runtime_error("Matrix Market entry out of range");
+        double x = 1.0;
+        if (!pattern) {
+            p = skip_ws(p);
+            char *end = nullptr;
+            x = std::strtod(p, &end);
+            if (end == p) throw std::runtime_error("Matrix Market entry without a value");
+            p = end;
+        }
+        p = next_line(p);
+        src.push_back((uint32_t)(i - 1));
+        dst.push_back((uint32_t)(j - 1));
+        if (weighted) val.push_back(x);
+        if (symmetric && i != j) {
+            src.push_back((uint32_t)(j - 1));
+            dst.push_back((uint32_t)(i - 1));
+            if (weighted) val.push_back(x);
+        }
+    }
+    return coo_to_csr(nrows, src, dst, val, weighted);
+}
+
+// ------------------------------------------------------------------------- .grb
+// SuiteSparse dump layout (graphio.h:88-105, 200-216, 549-606): 512-byte ASCII header, then
+// fmt:int32 kind:int32 hyper:f64 nrows,ncols:u64 nonempty:i64 nvec,nvals:u64 typecode:int32
+// typesize:size_t, then Ap[nvec+1] (Ah[nvec] if hypersparse) Ai[nvals] as uint64, then Ax
+// (one value if iso).  Only the sparse / hypersparse by-row forms are accepted.
+namespace {
+template <class T>
+void rd(FILE *f, T *dst, size_t count, const std::string &path)
+{
+    if (count && fread(dst, sizeof(T), count, f) != count) throw std::runtime_error("Truncated binary matrix file: " + path);
+}
+template <class T>
+void wr(FILE *f, const T *src, size_t count)
+{
+    if (count && fwrite(src, sizeof(T), count, f) != count) throw std::runtime_error("Write failed");
+}
+} // namespace
+
+HostMatrix ReadGrbFile(const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Cannot open binary matrix file: " + path);
+    HostMatrix A;
+    try {
+        char header[GRB_HEADER_LEN];
+        rd(f, header, GRB_HEADER_LEN, path);
+        int32_t fmt = 0, kind = 0, typecode = 0;
+        double hyper = 0;
+        uint64_t nrows = 0, ncols = 0, nvec = 0, nvals = 0, typesize = 0;
+        int64_t nonempty = 0;
+        rd(f, &fmt, 1, path); rd(f, &kind, 1, path); rd(f, &hyper, 1, path);
+        rd(f, &nrows, 1, path); rd(f, &ncols, 1, path); rd(f, &nonempty, 1, path);
+        rd(f, &nvec, 1, path); rd(f, &nvals, 1, path); rd(f, &typecode, 1, path); rd(f, &typesize, 1, path);
+        bool iso = false;
+        if (kind > 100) { iso = true; kind -= 100; }
+        const bool is_hyper = kind == 1, is_sparse = kind == 0 || kind == 2;
+        if (fmt != 0 || !(is_hyper || is_sparse)) throw std::runtime_error("Only by-row sparse .grb matrices are supported: " + path);
+        if (nrows != ncols) throw std::runtime_error("Adjacency matrix must be square");
+        if (!iso && typecode != 10) throw std::runtime_error("Non-iso .grb values must be FP64: " + path);
+        std::vector<GrB_Index> Ap(nvec + 1), Ah, Ai(nvals);
+        rd(f, Ap.data(), nvec + 1, path);
+        if (is_hyper) { Ah.resize(nvec); rd(f, Ah.data(), nvec, path); }
+        rd(f, Ai.data(), nvals, path);
+        A.nrows = nrows;
+        A.nvals = nvals;
+        A.iso = iso;
+        if (!iso) { A.Ax.resize(nvals); rd(f, A.Ax.data(), nvals, path); }
+        A.Ap.assign(nrows + 1, 0);
+        if (is_hyper) {
+            for (uint64_t k = 0; k < nvec; k++) A.Ap[Ah[k] + 1] = Ap[k + 1] - Ap[k];
+            for (uint64_t i = 0; i < nrows; i++) A.Ap[i + 1] += A.Ap[i];
+        } else {
+            if (nvec != nrows) throw std::runtime_error("Sparse .grb with nvec != nrows: " + path);
+            A.Ap = std::move(Ap);
+        }
+        A.Aj.resize(nvals);
+        for (uint64_t k = 0; k < nvals; k++) {
+            if (Ai[k] >= nrows) throw std::runtime_error("Column index out of range in " + path);
+            A.Aj[k] = (uint32_t)Ai[k];
+        }
+    } catch (...) {
+        fclose(f);
+        throw;
+    }
+    fclose(f);
+    return A;
+}
+
+void WriteGrbFile(const std::string &path, const HostMatrix &A)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot create binary matrix file: " + path);
+    try {
+        char header[GRB_HEADER_LEN];
+        const uint64_t typesize = A.iso ? 1 : 8;
+        int len = snprintf(header, GRB_HEADER_LEN,
+                           "SuiteSparse:GraphBLAS matrix\nv%-25s\nnrows:  %-18" PRIu64 "\nncols:  %-18" PRIu64
+                           "\nnvec:   %-18" PRIu64 "\nnvals:  %-18" PRIu64 "\nformat: %-8s\nsize:   %-18" PRIu64
+                           "\ntype:   %-72s\niso:    %1d\n%-210s\n\n",
+                           "7.4.4 (gxb200 converter)", A.nrows, A.nrows, A.nrows, A.nvals, "CSR ", typesize,
+                           A.iso ? "bool" : "double", A.iso ? 1 : 0, "\n");
+        if (len < 0) len = 0;
+        for (size_t k = (size_t)len; k < GRB_HEADER_LEN; k++) header[k] = ' ';
+        header[GRB_HEADER_LEN - 1] = '\0';
+        wr(f, header, GRB_HEADER_LEN);
+        const int32_t fmt = 0, kind = 2 + (A.iso ? 100 : 0), typecode = A.iso ? 0 : 10;
+        const double hyper = 0.0625;
+        const int64_t nonempty = -1;
+        const uint64_t n = A.nrows;
+        wr(f, &fmt, 1); wr(f, &kind, 1); wr(f, &hyper, 1); wr(f, &n, 1); wr(f, &n, 1); wr(f, &nonempty, 1);
+        wr(f, &n, 1); wr(f, &A.nvals, 1); wr(f, &typecode, 1); wr(f, &typesize, 1);
+        wr(f, A.Ap.data(), A.Ap.size());
+        std::vector<GrB_Index> Ai(A.Aj.begin(), A.Aj.end());
+        wr(f, Ai.data(), Ai.size());
+        if (A.iso) { const uint8_t one = 1; wr(f, &one, 1); }
+        else wr(f, A.Ax.data(), A.Ax.size());
+    } catch (...) {
+        fclose(f);
+        throw;
+    }
+    fclose(f);
+}
+
+// ------------------------------------------------------------------------- mappings
+std::vector<GrB_Index> ReadVtxFile(const std::string &path)
+{
+    FileBytes file(path);
+    std::vector<GrB_Index> mapping;
+    const char *p = file.data.data();
+    for (;;) {
+        while (*p == '\n' || *p == '\r' || *p == ' ') p++;
+        if (!*p) break;
+        mapping.push_back(parse_u64(p));
+        p = next_line(p);
+    }
+    return mapping;
+}
+
+std::vector<GrB_Index> ReadVtbFile(const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Cannot open binary mapping file: " + path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<GrB_Index> mapping((size_t)sz / sizeof(GrB_Index));
+    const size_t got = mapping.empty() ? 0 : fread(mapping.data(), sizeof(GrB_Index), mapping.size(), f);
+    fclose(f);
+    if (got != mapping.size()) throw std::runtime_error("Short read: " + path);
+    return mapping;
+}
+
+void WriteVtbFile(const std::string &path, const std::vector<GrB_Index> &mapping)
+{
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot create binary mapping file: " + path);
+    const size_t put = mapping.empty() ? 0 : fwrite(mapping.data(), sizeof(GrB_Index), mapping.size(), f);
+    fclose(f);
+    if (put != mapping.size()) throw std::runtime_error("Write failed: " + path);
+}
+
+HostMatrix ReadMatrixMarket(const BenchmarkParameters &parameters)
+{
+    ComputationTimer total_timer{"Loading the matrix"};
+    if (parameters.binary) return ReadGrbFile(parameters.input_dir + "/graph.grb");
+    return ReadMtxFile(parameters.input_dir + "/graph.mtx");
+}
+
+std::vector<GrB_Index> ReadMapping(const BenchmarkParameters &parameters)
+{
+    ComputationTimer timer{"Loading the mapping"};
+    if (parameters.binary) return ReadVtbFile(parameters.input_dir + "/graph.vtb");
+    return ReadVtxFile(parameters.input_dir + "/graph.vtx");
+}
+
+// ------------------------------------------------------------------------- result files
+ResultWriter::ResultWriter(const std::string &path) : buf_(1 << 22)
+{
+    f_ = fopen(path.c_str(), "w");
+}
+
+ResultWriter::~ResultWriter()
+{
+    if (f_) { flush(); fclose(f_); }
+}
+
+void ResultWriter::flush()
+{
+    if (used_) fwrite(buf_.data(), 1, used_, f_);
+    used_ = 0;
+}
+
+void ResultWriter::line_int(GrB_Index id, int64_t v)
+{
+    if (used_ + 64 > buf_.size()) flush();
+    used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %" PRId64 "\n", id, v);
+}
+
+void ResultWriter::line_uint(GrB_Index id, uint64_t v)
+{
+    if (used_ + 64 > buf_.size()) flush();
+    used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %" PRIu64 "\n", id, v);
+}
+
+void ResultWriter::line_sci(GrB_Index id, double v)
+{
+    if (used_ + 64 > buf_.size()) flush();
+    used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %.16e\n", id, v);
+}
+
+void ResultWriter::line_text(GrB_Index id, const char *s)
+{
+    if (used_ + 64 > buf_.size()) flush();
+    used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %s\n", id, s);
+}

@@ -1,0 +1,262 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+oracle on the same inputs.  Bars (BASELINE.json north_star): BFS levels, WCC
+and CDLP labels bit-exact; PageRank <= 1e-6 relative; LCC <= 1e-9 relative
+(integer ratio, one rounding); SSSP bit-exact (unique fix-point, see
+algo_sssp.cu) -- all far inside the Graphalytics validator's 1e-4."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_cases
+from helpers import golden, load_fixture, rel_err
+from ldbc_graphalytics_platforms_graphblas_b200 import rmat, validator
+from ldbc_graphalytics_platforms_graphblas_b200.graphio import HostGraph, csr_from_edges
+
+pytestmark = pytest.mark.gpu
+
+PR_TOL = 1e-6
+LCC_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi as c
+    c.init(0)
+    return c
+
+
+def check_all(capi, hg, iters_pr=10, iters_cdlp=10, src=None, what="bfs pr wcc cdlp lcc sssp"):
+    g = capi.Graph.from_host(hg)
+    n, rp, ci = hg.n, hg.rowptr, hg.colidx
+    if src is None:
+        src = rmat.max_out_degree_vertex(hg)
+    T = oracle.transpose(n, rp, ci) if hg.directed else None
+    try:
+        if "bfs" in what:
+            assert np.array_equal(g.bfs(src), oracle.bfs(n, rp, ci, src)), "bfs"
+        if "pr" in what:
+            out = g.pagerank(0.85, iters_pr)
+            ref = oracle.pagerank(n, rp, ci, 0.85, iters_pr, transposed=T)
+            assert rel_err(out, ref) <= PR_TOL, "pr"
+        if "wcc" in what:
+            assert np.array_equal(g.wcc(), oracle.wcc(n, rp, ci, hg.directed, transposed=T)), "wcc"
+        if "cdlp" in what:
+            assert np.array_equal(g.cdlp(iters_cdlp), oracle.cdlp(n, rp, ci, hg.directed, iters_cdlp, transposed=T)), "cdlp"
+        if "lcc" in what:
+            assert rel_err(g.lcc(), oracle.lcc(n, rp, ci, hg.directed, transposed=T)) <= LCC_TOL, "lcc"
+        if "sssp" in what and hg.weights is not None:
+            assert np.array_equal(g.sssp(src), oracle.sssp(n, rp, ci, hg.weights, src)), "sssp"
+    finally:
+        g.free()
+
+
+# ------------------------------------------------------------------ the reference's own fixtures
+@pytest.mark.parametrize("name,alg", golden_cases())
+def test_golden_fixture(capi, name, alg):
+    hg, params = load_fixture(name)
+    ids, ref = golden(name, alg)
+    g = capi.Graph.from_host(hg)
+    try:
+        if alg == "BFS":
+            out = g.bfs(hg.dense_id(params["bfs_source"]))
+        elif alg == "PR":
+            out = g.pagerank(params["pr_damping"], params["pr_iters"])
+        elif alg == "WCC":
+            out = hg.mapping[g.wcc().astype(np.int64)]
+        elif alg == "CDLP":
+            out = hg.mapping[g.cdlp(params["cdlp_iters"]).astype(np.int64)]
+        elif alg == "LCC":
+            out = g.lcc()
+        else:
+            out = g.sssp(hg.dense_id(params["sssp_source"]))
+    finally:
+        g.free()
+    assert validator.validate(alg, out, ref)
+    if alg in ("BFS", "WCC", "CDLP"):
+        assert np.array_equal(np.asarray(out, dtype=np.int64), ref)
+    elif alg == "PR":
+        assert rel_err(out, ref) <= 5e-6
+    else:
+        assert rel_err(out, ref) <= 1e-11
+
+
+# ------------------------------------------------------------------ random graphs
+def random_graph(n, m, directed, seed, weighted=True):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n, m)
+    dst = rng.integers(0, n, m)
+    w = rng.random(m) + 1e-3 if weighted else None
+    return csr_from_edges(n, src, dst, w, directed)
+
+
+@pytest.mark.parametrize("n,m,directed,seed", [
+    (1, 0, True, 1), (2, 1, False, 2), (33, 40, True, 3), (64, 300, False, 4), (1000, 5000, True, 5),
+    (1000, 5000, False, 6), (5000, 200000, True, 7), (5000, 200000, False, 8), (100000, 150000, True, 9),
+])
+def test_random_graphs(capi, n, m, directed, seed):
+    check_all(capi, random_graph(n, m, directed, seed))
+
+
+def test_empty_rows_and_isolated_vertices(capi):
+    # vertices 40..99 are isolated; n is not a multiple of 32
+    hg = random_graph(40, 120, True, 11)
+    rp = np.concatenate([hg.rowptr, np.full(60, hg.rowptr[-1], dtype=np.uint64)])
+    check_all(capi, HostGraph(100, rp, hg.colidx, hg.weights, True), src=3)
+
+
+@pytest.mark.parametrize("directed", [True, False])
+def test_hub_rows(capi, directed):
+    """Star + noise: one vertex with 20000 neighbours exercises the chunked long-row paths
+    (PR/WCC/BFS/SSSP CHUNK pieces, CDLP spill tables), mid rows the warp-per-row paths."""
+    n = 30000
+    rng = np.random.default_rng(5)
+    hub = np.zeros(20000, dtype=np.int64)
+    leaves = rng.choice(np.arange(1, n), 20000, replace=False)
+    mid_src = np.repeat(np.arange(1, 41), 600)           # 40 rows with ~600 entries
+    mid_dst = rng.integers(1, n, mid_src.size)
+    noise_s = rng.integers(0, n, 60000)
+    noise_d = rng.integers(0, n, 60000)
+    src = np.concatenate([hub, leaves[:5000], mid_src, noise_s])
+    dst = np.concatenate([leaves, hub[:5000], mid_dst, noise_d])
+    w = rng.random(src.size) + 1e-3
+    check_all(capi, csr_from_edges(n, src, dst, w, directed), src=0)
+
+
+def test_unreachable_hub_in_pull(capi):
+    """A vertex with a long in-list that BFS never reaches is scanned by the warp-per-row pull."""
+    n = 5000
+    rng = np.random.default_rng(9)
+    comp = rng.integers(0, 2500, (40000, 2))                       # component A: ids < 2500
+    into_hub = np.stack([np.arange(2600, 4600), np.full(2000, 2550)], 1)  # 2000 unreachable sources -> 2550
+    e = np.concatenate([comp, into_hub])
+    hg = csr_from_edges(n, e[:, 0], e[:, 1], None, True)
+    check_all(capi, hg, src=int(np.argmax(np.diff(hg.rowptr.astype(np.int64))[:2500])), what="bfs wcc")
+
+
+@pytest.mark.parametrize("scale,directed", [(10, True), (10, False), (14, True), (14, False), (16, True), (16, False)])
+def test_rmat_small(capi, scale, directed):
+    check_all(capi, rmat.rmat_graph(scale, directed, weighted=True))
+
+
+def test_u64_and_u32_entry_points_agree(capi):
+    hg = rmat.rmat_graph(12, True, weighted=True)
+    g64 = capi.Graph.from_csr(hg.n, hg.rowptr, hg.colidx.astype(np.uint64), hg.weights, True)
+    g32 = capi.Graph.from_csr(hg.n, hg.rowptr, hg.colidx, hg.weights, True)
+    try:
+        for a, b in zip(g64.download(), g32.download()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(g64.cdlp(5), g32.cdlp(5))
+    finally:
+        g64.free()
+        g32.free()
+
+
+def test_unsorted_rows_are_sorted_on_upload(capi):
+    hg = rmat.rmat_graph(11, True, weighted=True)
+    rng = np.random.default_rng(3)
+    ci, w = hg.colidx.copy(), hg.weights.copy()
+    rp = hg.rowptr.astype(np.int64)
+    for v in range(hg.n):
+        p = rng.permutation(rp[v + 1] - rp[v]) + rp[v]
+        ci[rp[v]:rp[v + 1]], w[rp[v]:rp[v + 1]] = ci[p], w[p]
+    g = capi.Graph.from_csr(hg.n, hg.rowptr, ci, w, True)
+    try:
+        rp2, ci2, w2 = g.download()
+        assert np.array_equal(ci2, hg.colidx) and np.array_equal(w2, hg.weights)
+    finally:
+        g.free()
+
+
+def test_invalid_input_is_rejected(capi):
+    rp = np.array([0, 1, 2], dtype=np.uint64)
+    with pytest.raises(capi.GxError):
+        capi.Graph.from_csr(2, rp, np.array([1, 7], dtype=np.uint32))      # column id >= n
+    with pytest.raises(capi.GxError):
+        capi.Graph.from_csr(2, np.array([0, 2, 1], dtype=np.uint64), np.array([1, 0], dtype=np.uint32))
+    g = capi.Graph.from_csr(2, rp, np.array([1, 0], dtype=np.uint32))
+    try:
+        with pytest.raises(capi.GxError):
+            g.bfs(5)                                                        # source out of range
+        with pytest.raises(capi.GxError):
+            g.sssp(0)                                                       # unweighted graph
+    finally:
+        g.free()
+
+
+# ------------------------------------------------------------------ device generator
+@pytest.mark.parametrize("scale,directed,weighted", [(10, True, False), (13, False, True), (16, True, True)])
+def test_device_rmat_matches_host_generator(capi, scale, directed, weighted):
+    hg = rmat.rmat_graph(scale, directed, weighted)
+    g = capi.Graph.rmat(scale, directed, weighted)
+    try:
+        assert (g.n, g.nnz) == (hg.n, hg.nnz)
+        rp, ci, w = g.download()
+        assert np.array_equal(rp, hg.rowptr) and np.array_equal(ci, hg.colidx)
+        assert np.array_equal(g.mapping, hg.mapping)
+        if weighted:
+            assert np.array_equal(w, hg.weights)
+        assert g.max_degree_vertex() == rmat.max_out_degree_vertex(hg)
+    finally:
+        g.free()
+
+
+# ------------------------------------------------------------------ benchmark-size graphs
+@pytest.fixture(scope="module")
+def rmat20(capi):
+    out = {}
+    for directed in (True, False):
+        g = capi.Graph.rmat(20, directed, weighted=True)
+        rp, ci, w = g.download()
+        out[directed] = (g, HostGraph(g.n, rp, ci, w, directed, g.mapping))
+    yield out
+    for g, _ in out.values():
+        g.free()
+
+
+@pytest.mark.parametrize("directed", [True, False])
+def test_rmat20_against_oracle(capi, rmat20, directed):
+    g, hg = rmat20[directed]
+    n, rp, ci = hg.n, hg.rowptr, hg.colidx
+    src = g.max_degree_vertex()
+    T = oracle.transpose(n, rp, ci) if directed else None
+    assert np.array_equal(g.bfs(src), oracle.bfs(n, rp, ci, src))
+    assert rel_err(g.pagerank(0.85, 10), oracle.pagerank(n, rp, ci, 0.85, 10, transposed=T)) <= PR_TOL
+    assert np.array_equal(g.wcc(), oracle.wcc(n, rp, ci, directed, transposed=T))
+    assert np.array_equal(g.cdlp(10), oracle.cdlp(n, rp, ci, directed, 10, transposed=T))
+    assert np.array_equal(g.sssp(src), oracle.sssp(n, rp, ci, hg.weights, src))
+    # LCC: the oracle's cost is quadratic in hub degrees, so spot-check a sample incl. the top hubs
+    deg = np.diff(rp.astype(np.int64))
+    rng = np.random.default_rng(1)
+    sample = np.unique(np.concatenate([np.argsort(deg)[-4:], rng.integers(0, n, 3000)])).astype(np.uint64)
+    ref = oracle.lcc(n, rp, ci, directed, transposed=T, subset=sample)
+    out = g.lcc()
+    assert rel_err(out[sample.astype(np.int64)], ref[sample.astype(np.int64)]) <= LCC_TOL
+
+
+def test_rmat22_size_independent_properties(capi):
+    """BASELINE config [1]: RMAT-22 directed, BFS + PR.  Full-size checks that do not need the
+    oracle: PR mass conservation and positivity, BFS level consistency along every edge."""
+    g = capi.Graph.rmat(22, True)
+    try:
+        rp, ci, _ = g.download()
+        n = g.n
+        src = g.max_degree_vertex()
+        pr = g.pagerank(0.85, 10)
+        assert abs(pr.sum() - 1.0) < 1e-9 and (pr > 0).all()
+        lvl = g.bfs(src)
+        assert lvl[src] == 0
+        rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp.astype(np.int64)))
+        lu, lv = lvl[rows], lvl[ci.astype(np.int64)]
+        reach = lu != capi.UNREACHED
+        assert (lv[reach] != capi.UNREACHED).all(), "a reached vertex has only reached out-neighbours"
+        assert (lv[reach] <= lu[reach] + 1).all(), "levels grow by at most one along an edge"
+        # every reached non-source vertex has an in-neighbour exactly one level up
+        best = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+        np.minimum.at(best, ci.astype(np.int64)[reach], lu[reach] + 1)
+        others = (lvl != capi.UNREACHED) & (np.arange(n) != src)
+        assert np.array_equal(best[others], lvl[others])
+        # and the oracle agrees at this size too (a few seconds of CPU)
+        assert np.array_equal(lvl, oracle.bfs(n, rp, ci, src))
+        assert rel_err(pr, oracle.pagerank(n, rp, ci, 0.85, 10)) <= PR_TOL
+    finally:
+        g.free()

@@ -1,0 +1,104 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the
+header declares, the host file formats round-trip, the converter binary writes the
+SuiteSparse dump layout, the binaries fail loudly without a device, and the
+world_size-2 sharding logic agrees across ranks."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from helpers import load_fixture
+from ldbc_graphalytics_platforms_graphblas_b200 import graphio, rmat, validator
+
+EXE = os.path.join(ROOT, "bin", "exe")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__
+    __graft_entry__.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    header = open(capi.HEADER_PATH).read()
+    declared = set(re.findall(r"^(?:int|void|const char \*)\s*\*?(gx_\w+)\(", header, flags=re.M))
+    assert len(declared) >= 28
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in gxb200.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gx_\w+)", out))
+    assert declared <= exported
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.GxError):
+        capi.init(0)
+    with pytest.raises(capi.GxError):
+        capi.Graph.from_csr(2, np.array([0, 1, 2], dtype=np.uint64), np.array([1, 0], dtype=np.uint32))
+    r = subprocess.run([os.path.join(EXE, "pr"), "--input-dir", "/nonexistent", "--output-file", "/tmp/x"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ldbc_graphalytics_platforms_graphblas_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dp, f), errors="replace").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b|liboracle", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("name", ["example-directed", "example-undirected", "test-wcc-directed"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_relabel_and_readers_roundtrip(tmp_path, name, weighted):
+    g, params = load_fixture(name)
+    if weighted and not params["weighted"]:
+        pytest.skip("unweighted fixture")
+    graphio.write_vtx_mtx(str(tmp_path), os.path.join(GOLDEN, name + ".v"), os.path.join(GOLDEN, name + ".e"),
+                          params["directed"], weighted)
+    head = open(tmp_path / "graph.mtx").read().split("\n")
+    assert head[0] == "%%MatrixMarket matrix coordinate {} {}".format(
+        "real" if weighted else "integer", "general" if params["directed"] else "symmetric")
+    assert head[1] == "%%GraphBLAS " + ("GrB_FP64" if weighted else "GrB_BOOL")
+    h = graphio.read_vtx_mtx(str(tmp_path))
+    assert np.array_equal(h.rowptr, g.rowptr) and np.array_equal(h.colidx, g.colidx)
+    assert np.array_equal(h.mapping, g.mapping)
+    if weighted:
+        assert np.array_equal(h.weights, g.weights)
+    # C++ converter (GraphBLAS-free tools/converter.cpp) -> SuiteSparse dump layout, read by the numpy reader
+    subprocess.check_call([os.path.join(EXE, "converter"), "--data-dir", str(tmp_path)])
+    b = graphio.read_grb(str(tmp_path / "graph.grb"), params["directed"])
+    assert np.array_equal(b.rowptr, g.rowptr) and np.array_equal(b.colidx, g.colidx)
+    assert (b.weights is None) == (not weighted)
+    if weighted:
+        assert np.array_equal(b.weights, g.weights)
+    assert np.array_equal(np.fromfile(tmp_path / "graph.vtb", dtype="<u8"), g.mapping)
+    assert os.path.getsize(tmp_path / "graph.grb") == 512 + 68 + 8 * (g.n + 1) + 8 * g.nnz + (8 * g.nnz if weighted else 1)
+
+
+def test_numpy_grb_writer_matches_cpp_reader_layout(tmp_path):
+    g = rmat.rmat_graph(8, directed=True, weighted=True)
+    graphio.write_graph_dir(str(tmp_path), g, binary=True)
+    b = graphio.read_grb(str(tmp_path / "graph.grb"), True)
+    assert np.array_equal(b.colidx, g.colidx) and np.array_equal(b.weights, g.weights)
+    graphio.write_graph_dir(str(tmp_path), g, binary=False)
+    h = graphio.read_vtx_mtx(str(tmp_path))
+    assert np.array_equal(h.colidx, g.colidx) and np.array_equal(h.weights, g.weights)
+
+
+def test_validator_rules():
+    assert validator.validate("bfs", [0, 1, 2], [0, 1, 2]) and not validator.validate("bfs", [0, 1, 3], [0, 1, 2])
+    assert validator.validate("wcc", [5, 5, 9], [1, 1, 2]) and not validator.validate("wcc", [5, 5, 5], [1, 1, 2])
+    assert not validator.validate("cdlp", [1, 2, 3], [1, 1, 2])
+    assert validator.validate("pr", [1.0, 2.00001], [1.0, 2.0]) and not validator.validate("pr", [1.0, 2.001], [1.0, 2.0])
+    assert validator.validate("sssp", [np.inf, 1.0], [np.inf, 1.0]) and not validator.validate("sssp", [5.0, 1.0], [np.inf, 1.0])
+    assert np.array_equal(validator.canonical_min_labels([7, 7, 3, 3, 7]), [0, 0, 2, 2, 0])
