@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- EVPS of the Graphalytics hot path on synthetic Graph500 RMAT graphs.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU reference arm
+
+Workload (BASELINE.json configs[1]): BFS + PageRank (d = 0.85, 10 iterations) on the
+directed RMAT scale-22 (edgefactor 16) graph per GPU; with N GPUs the scale grows by
+log2(N) (weak scaling) and the graph is 1-D row partitioned over the ranks.  A step is
+one BFS plus one PageRank over the resident graph.  EVPS = (|V| + |E|) / T per
+algorithm (Graphalytics' definition); `value` is the job figure 2(|V|+|E|) / (T_bfs +
+T_pr), i.e. the harmonic mean of the two per-algorithm EVPS, which are listed under
+`per_algorithm`.  One JSON line on stdout (rank 0); progress goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PR_DAMPING, PR_ITERS = 0.85, 10
+BASE_SCALE, EDGEFACTOR = 22, 16
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------- CPU legs
+def cpu_workload(oracle, n, rp, ci, src, pr_iters=PR_ITERS):
+    """One BFS + one PageRank of the CPU restatement, timed over the reference's own window:
+    PageRank includes the transpose (LAGraph_Cached_AT inside pr.cpp:58-61)."""
+    t0 = time.perf_counter()
+    oracle.bfs(n, rp, ci, src)
+    t1 = time.perf_counter()
+    oracle.pagerank(n, rp, ci, PR_DAMPING, pr_iters)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def host_rmat(scale):
+    """CPU-only construction of the benchmark graph (the reference arm never touches the GPU)."""
+    import oracle
+    from ldbc_graphalytics_platforms_graphblas_b200 import rmat
+    from ldbc_graphalytics_platforms_graphblas_b200.graphio import csr_from_edges
+    seed = rmat.default_seed(scale)
+    src, dst = oracle.rmat_edges(scale, seed, 0, EDGEFACTOR << scale)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    ids = np.unique(np.concatenate([src, dst]))
+    g = csr_from_edges(ids.size, np.searchsorted(ids, src), np.searchsorted(ids, dst), None, True, mapping=ids)
+    return g
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from ldbc_graphalytics_platforms_graphblas_b200 import rmat
+    scale = args.scale or BASE_SCALE + int(np.log2(args.gpus))
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)
+    log(f"[reference] building RMAT-{scale} on the host ({cores} threads)")
+    g = host_rmat(scale)
+    n, m = g.n, g.nnz
+    src = rmat.max_out_degree_vertex(g)
+    # bound the step so that the whole run ends within a few minutes: a probe run decides how many
+    # PageRank iterations one step executes; the time is scaled back to 10 iterations
+    tb, tp = cpu_workload(oracle, n, g.rowptr, g.colidx, src, 1)
+    budget = 200.0 / max(args.steps + args.warmup, 1)
+    est_full = tb + tp + 9 * max(tp * 0.25, 1e-3)
+    iters = PR_ITERS if est_full <= budget else max(1, min(PR_ITERS, int((budget - tb - tp) / max(tp * 0.25, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_workload(oracle, n, g.rowptr, g.colidx, src, iters)
+    t_bfs = t_pr = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = cpu_workload(oracle, n, g.rowptr, g.colidx, src, iters)
+        t_bfs += a
+        t_pr += b
+    wall = time.perf_counter() - t0
+    t_bfs /= args.steps
+    t_pr /= args.steps
+    if iters != PR_ITERS:
+        # transpose + per-iteration cost, extrapolated linearly to the 10 iterations of the config
+        one = cpu_workload(oracle, n, g.rowptr, g.colidx, src, 1)[1]
+        per_iter = max((t_pr - one) / max(iters - 1, 1), 0.0) if iters > 1 else one * 0.25
+        t_pr = one + per_iter * (PR_ITERS - 1)
+    ev = n + m
+    value = 2 * ev / (t_bfs + t_pr)
+    sample = (f"full workload per step (BFS + transpose + {PR_ITERS} PageRank iterations)" if iters == PR_ITERS else
+              f"BFS + transpose + {iters} PageRank iterations per step, PageRank time extrapolated to {PR_ITERS}")
+    line = {
+        "impl": "reference", "metric": "EVPS (BFS+PR, harmonic mean of per-algorithm EVPS)", "value": value,
+        "unit": "edges+vertices/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (t_bfs + t_pr), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BFS + PageRank(d=0.85, {PR_ITERS} it) on directed Graph500 RMAT scale-{scale} ef={EDGEFACTOR}",
+                   "vertices": n, "edges": m, "bfs_source": "max out-degree vertex"},
+        "per_algorithm": {"bfs": {"evps": ev / t_bfs, "ms": 1e3 * t_bfs}, "pr": {"evps": ev / t_pr, "ms": 1e3 * t_pr}},
+        "cpu_baseline": {"value": value, "unit": "edges+vertices/s", "cores": cores, "kind": "port",
+                         "sample": sample + "; LAGraph-equivalent OpenMP restatement (oracle/oracle.c), "
+                                            "GraphBLAS/LAGraph are not installable here"},
+        "e2e": {"value": value, "unit": "edges+vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.init(local)
+    if world > 1:
+        import torch
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        capi.comm_init(rank, world, uid[0])
+
+    def barrier():
+        capi.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    scale = args.scale or BASE_SCALE + int(np.log2(world))
+    peak, peak_src = measured_peak()
+    t0 = time.perf_counter()
+    g = capi.Graph.rmat(scale, directed=True, weighted=False, want_mapping=False)
+    n, m = g.n, g.nnz
+    ev = n + m
+    src = g.max_degree_vertex()
+    g.cache(capi.GX_CACHE_AT)
+    log(f"[rank {rank}] RMAT-{scale}: n={n} m={m} src={src} built in {time.perf_counter() - t0:.2f}s")
+
+    def step(out_b=False, out_p=False):
+        g.bfs(src, out=out_b)
+        tb = capi.last_timing()
+        g.pagerank(PR_DAMPING, PR_ITERS, out=out_p)
+        tp = capi.last_timing()
+        return tb, tp
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident timing: inputs already in HBM, results stay in HBM ----------------
+    barrier()
+    capi.timer_start()
+    kb = kp = 0.0
+    launches = 0
+    bytes_b = bytes_p = 0
+    for _ in range(args.steps):
+        tb, tp = step()
+        kb += tb["kernel_ms"]; kp += tp["kernel_ms"]
+        launches += tb["kernel_launches"] + tp["kernel_launches"]
+        bytes_b, bytes_p = tb["algorithmic_bytes"], tp["algorithmic_bytes"]
+        bfs_levels, bfs_inspected = tb["iterations"], tb["edges_inspected"]
+    t_dev_ms = capi.timer_stop()
+    barrier()
+    t_dev_ms = max_over_ranks(t_dev_ms)
+    ms_per_step = t_dev_ms / args.steps
+    value = 2 * ev / (ms_per_step * 1e-3)
+
+    # ---- per-kernel pass (CUDA event pair around every launch, separate from the timed region)
+    capi.profile(True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        step()
+    capi.profile(False)
+    prof = capi.profile_report()
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    rp_h, ci_h, _ = g.download()
+    pin_rp = capi.PinnedArray((n + 1,), np.uint64); pin_rp.array[:] = rp_h
+    pin_ci = capi.PinnedArray((m,), np.uint32); pin_ci.array[:] = ci_h
+    pin_lvl = capi.PinnedArray((n,), np.int64)
+    pin_rank = capi.PinnedArray((n,), np.float64)
+
+    def e2e_step():
+        h = capi.Graph.from_csr(n, pin_rp.array, pin_ci.array, None, True)   # H2D upload + validation
+        h.bfs(src, out=pin_lvl.array)                                           # builds A' on first use, D2H levels
+        h.pagerank(PR_DAMPING, PR_ITERS, out=pin_rank.array)                    # D2H ranks
+        h.free()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    capi.sync()
+    t_e2e = max_over_ranks(time.perf_counter() - t1) / e2e_steps
+    clocks = sampler.stop() if sampler else None
+    e2e = {"value": 2 * ev / t_e2e, "unit": "edges+vertices/s", "ms_per_step": 1e3 * t_e2e,
+           "h2d_bytes_per_step": int(8 * (n + 1) + 4 * m), "d2h_bytes_per_step": int(16 * n),
+           "entry": "gx_graph_create_csr32 + gx_bfs + gx_pagerank + gx_graph_free, pinned host buffers",
+           "steps": e2e_steps}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    pr_iter_bytes = 4 * m + 8 * (n + 1) + 28 * n            # SURVEY.md 8(d), per PageRank iteration
+    top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
+    total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
+    pr_kernels = {k: v for k, v in prof.items() if k.startswith("k_pr_")}
+    pr_ms_per_iter = sum(v[1] for v in pr_kernels.values()) / (prof_steps * PR_ITERS)
+    roof = {"bound": "hbm", "kernel": "PageRank iteration (" + "+".join(sorted(pr_kernels)) + ")",
+            "achieved": pr_iter_bytes / (pr_ms_per_iter * 1e-3) / 1e9 if pr_ms_per_iter else None,
+            "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "bytes_per_launch": pr_iter_bytes, "launch_ms": pr_ms_per_iter,
+            "share_of_step": sum(v[1] for v in pr_kernels.values()) / total_prof_ms, "traffic": None,
+            "top_kernel": top[0], "top_kernel_share": top[1][1] / total_prof_ms}
+    roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        oracle.set_threads(cores)
+        best = None
+        for _ in range(2):
+            a, b = cpu_workload(oracle, n, rp_h, ci_h, src)
+            if best is None or a + b < sum(best):
+                best = (a, b)
+        cpu = {"value": 2 * ev / sum(best), "unit": "edges+vertices/s", "cores": cores, "kind": "port",
+               "sample": f"full workload, best of 2: BFS {best[0]:.3f}s + PageRank incl. transpose {best[1]:.3f}s "
+                         f"(LAGraph-equivalent OpenMP restatement, oracle/oracle.c)",
+               "bfs_evps": ev / best[0], "pr_evps": ev / best[1]}
+
+    line = {
+        "metric": "EVPS (BFS+PR, harmonic mean of per-algorithm EVPS)", "value": value, "unit": "edges+vertices/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BFS + PageRank(d=0.85, {PR_ITERS} it) on directed Graph500 RMAT scale-{scale} ef={EDGEFACTOR}",
+                   "vertices": n, "edges": m, "bfs_source": "max out-degree vertex",
+                   "l2_policy": "inputs larger than L2 (adjacency 2 x 4m bytes >> 126 MB), no flush",
+                   "partition": "single GPU" if world == 1 else f"1-D row blocks over {world} ranks"},
+        "per_algorithm": {
+            "bfs": {"evps": ev / (kb / args.steps * 1e-3), "kernel_ms": kb / args.steps, "levels": bfs_levels,
+                    "edges_inspected": bfs_inspected, "algorithmic_bytes": bytes_b,
+                    "hbm_frac": bytes_b / (kb / args.steps * 1e-3) / 1e9 / peak},
+            "pr": {"evps": ev / (kp / args.steps * 1e-3), "kernel_ms": kp / args.steps, "iterations": PR_ITERS,
+                   "algorithmic_bytes": bytes_p, "hbm_frac": bytes_p / (kp / args.steps * 1e-3) / 1e9 / peak}},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "kernels": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in prof.items()},
+    }
+    print(json.dumps(line), flush=True)
+    g.free()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gxb200", choices=["gxb200", "reference"])
+    ap.add_argument("--scale", type=int, default=0, help="override the RMAT scale (default 22 + log2(gpus))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

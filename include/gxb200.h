@@ -130,6 +130,11 @@ int gx_timer_stop(double *elapsed_ms);
 int gx_sync(void);
 /* Overwrites a buffer larger than L2 (126 MB) so the next timed step starts cold. */
 int gx_flush_l2(void);
+/* Per-kernel timing session (CUDA event pair around every launch on the library stream).
+ * gx_profile(1) clears and starts, gx_profile(0) stops; the report is one line per kernel,
+ * "<name>\t<launches>\t<total ms>\n", sorted by total time. */
+int gx_profile(int enable);
+const char *gx_profile_report(void);
 /* Pinned host memory for callers that want full-speed uploads. */
 int gx_host_alloc(void **p, uint64_t bytes);
 int gx_host_free(void *p);

@@ -61,7 +61,7 @@ def lib():
             "gx_bfs": [vp, u64, vp], "gx_pagerank": [vp, dbl, i32, vp], "gx_wcc": [vp, vp],
             "gx_cdlp": [vp, i32, vp], "gx_lcc": [vp, vp], "gx_sssp": [vp, u64, vp],
             "gx_last_timing": [ctypes.POINTER(Timing)], "gx_timer_start": [], "gx_timer_stop": [ctypes.POINTER(dbl)],
-            "gx_sync": [], "gx_flush_l2": [], "gx_host_alloc": [pp, u64], "gx_host_free": [vp],
+            "gx_sync": [], "gx_flush_l2": [], "gx_profile": [i32], "gx_host_alloc": [pp, u64], "gx_host_free": [vp],
             "gx_rmat_create": [pp, i32, i32, u64, i32, i32, pp], "gx_graph_max_degree_vertex": [vp, ctypes.POINTER(u64)],
         }
         for name, args in sig.items():
@@ -69,6 +69,7 @@ def lib():
             f.argtypes = args
             f.restype = i32
         L.gx_last_error.restype = ctypes.c_char_p
+        L.gx_profile_report.restype = ctypes.c_char_p
         L.gx_free_host.argtypes = [vp]
         L.gx_free_host.restype = None
         _lib = L
@@ -118,6 +119,19 @@ def sync():
 
 def flush_l2():
     _chk(lib().gx_flush_l2())
+
+
+def profile(enable):
+    _chk(lib().gx_profile(int(bool(enable))))
+
+
+def profile_report():
+    """{kernel name: (launches, total ms)} of the current profiling session."""
+    out = {}
+    for line in lib().gx_profile_report().decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name.strip("()")] = (int(cnt), float(ms))
+    return out
 
 
 def comm_unique_id():

@@ -1,8 +1,11 @@
 // api.cu -- context, error reporting, stopwatch, pinned memory, NCCL communicator.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -27,6 +30,49 @@ void read_back(void *host_dst, const void *dev_src, size_t bytes)
     GX_CUDA(cudaMemcpyAsync(c.pinned_scratch, dev_src, bytes, cudaMemcpyDeviceToHost, c.stream));
     GX_CUDA(cudaStreamSynchronize(c.stream));
     memcpy(host_dst, c.pinned_scratch, bytes);
+}
+
+// ----------------------------------------------------------------------------- profiler
+struct ProfAgg { double ms = 0; uint64_t count = 0; };
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_ev_pool;
+static std::vector<std::pair<const char *, std::pair<cudaEvent_t, cudaEvent_t>>> g_pending;
+static std::map<std::string, ProfAgg> g_agg;
+static std::string g_prof_text;
+
+bool profiling() { return g_prof_on; }
+
+static cudaEvent_t prof_event()
+{
+    if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    GX_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
+void prof_begin(const char *name)
+{
+    cudaEvent_t a = prof_event(), b = prof_event();
+    g_pending.push_back({name, {a, b}});
+    GX_CUDA(cudaEventRecord(a, ctx().stream));
+}
+
+void prof_end() { GX_CUDA(cudaEventRecord(g_pending.back().second.second, ctx().stream)); }
+
+static void prof_collect()
+{
+    if (g_pending.empty()) return;
+    GX_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (auto &p : g_pending) {
+        float ms = 0;
+        GX_CUDA(cudaEventElapsedTime(&ms, p.second.first, p.second.second));
+        ProfAgg &a = g_agg[p.first];
+        a.ms += ms;
+        a.count++;
+        g_ev_pool.push_back(p.second.first);
+        g_ev_pool.push_back(p.second.second);
+    }
+    g_pending.clear();
 }
 
 __global__ void k_flush(uint4 *__restrict__ buf, size_t n16, uint32_t tag)
@@ -163,6 +209,32 @@ extern "C" int gx_flush_l2(void)
         k_flush<<<grid_persistent(8), 256, 0, c.stream>>>((uint4 *)c.flush_buf, c.flush_bytes / 16, ++tag);
         GX_CUDA(cudaGetLastError());
     });
+}
+
+// gx_profile(1) starts a fresh per-kernel timing session, gx_profile(0) stops it.
+extern "C" int gx_profile(int enable)
+{
+    return guarded([&] {
+        require_ready();
+        prof_collect();
+        if (enable) g_agg.clear();
+        g_prof_on = enable != 0;
+    });
+}
+
+// "<kernel name>\t<launches>\t<total ms>\n" per kernel, sorted by total time (descending).
+extern "C" const char *gx_profile_report(void)
+{
+    g_prof_text.clear();
+    try {
+        prof_collect();
+    } catch (...) {
+        return "";
+    }
+    std::vector<std::pair<std::string, ProfAgg>> v(g_agg.begin(), g_agg.end());
+    std::sort(v.begin(), v.end(), [](const auto &x, const auto &y) { return x.second.ms > y.second.ms; });
+    for (auto &e : v) g_prof_text += e.first + "\t" + std::to_string(e.second.count) + "\t" + std::to_string(e.second.ms) + "\n";
+    return g_prof_text.c_str();
 }
 
 extern "C" int gx_host_alloc(void **p, uint64_t bytes)

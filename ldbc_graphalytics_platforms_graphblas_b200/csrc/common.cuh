@@ -75,10 +75,20 @@ void require_ready();
 
 inline void count_launch(unsigned k = 1) { ctx().timing.kernel_launches += k; }
 
+// Optional per-kernel timing (gx_profile): a CUDA event pair around every launch on the
+// library stream, aggregated by kernel name.  Off by default (it costs two event records per
+// launch); bench.py switches it on for a separate pass to get the dominant kernel's duration.
+bool profiling();
+void prof_begin(const char *name);
+void prof_end();
+
 // Launch wrapper: counts the launch and checks the launch status.
 #define GX_LAUNCH(kernel, grid, block, smem, ...)                                              \
     do {                                                                                       \
+        const bool prof__ = ::gx::profiling();                                                 \
+        if (prof__) ::gx::prof_begin(#kernel);                                                 \
         kernel<<<(grid), (block), (smem), ::gx::ctx().stream>>>(__VA_ARGS__);                  \
+        if (prof__) ::gx::prof_end();                                                          \
         ::gx::count_launch();                                                                  \
         GX_CUDA(cudaGetLastError());                                                           \
     } while (0)

@@ -52,16 +52,21 @@ __global__ void k_validate(const uint64_t *__restrict__ rowptr, const uint32_t *
     (void)unsorted;
 }
 
-// one thread per row: is the row sorted (non-decreasing)?
+// Entry-parallel sortedness check: a decrease col[e] < col[e-1] is legal only where a row
+// starts at e, which a binary search in rowptr decides (decreases are rare: ~one per row).
 __global__ void k_check_sorted(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n,
-                               int *__restrict__ unsorted)
+                               uint64_t m, int *__restrict__ unsorted)
 {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; v < n; v += stride) {
-        uint64_t a = rowptr[v], b = rowptr[v + 1];
-        for (uint64_t e = a + 1; e < b; e++)
-            if (col[e] < col[e - 1]) { *unsorted = 1; break; }
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) {
+        if (col[e] >= col[e - 1]) continue;
+        uint64_t lo = 0, hi = n; // is there a row r with rowptr[r] == e ?
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] < e) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= n || rowptr[lo] != e) *unsorted = 1;
     }
 }
 
@@ -176,7 +181,7 @@ void finish_graph(gx_graph *g)
     DevBuf<int> flags(2);
     flags.zero();
     GX_LAUNCH(k_validate, grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->n, g->m, flags.p, flags.p + 1);
-    GX_LAUNCH(k_check_sorted, grid_for(g->n, 256), 256, 0, g->out.rowptr.p, g->out.col.p, g->n, flags.p + 1);
+    GX_LAUNCH(k_check_sorted, grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->n, g->m, flags.p + 1);
     int h[2] = {0, 0};
     read_back(h, flags.p, sizeof(h));
     if (h[0]) throw Error(GX_ERR_INVALID, "CSR arrays are inconsistent (rowptr not monotone or column id >= n)");

@@ -19,6 +19,13 @@ __global__ void k_collect_long(const uint64_t *__restrict__ rowptr, uint64_t n, 
     }
 }
 
+__global__ void k_gather_pairs(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ rows, uint64_t count,
+                               uint64_t *__restrict__ pairs)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) { pairs[2 * i] = rowptr[rows[i]]; pairs[2 * i + 1] = rowptr[rows[i] + 1]; }
+}
+
 void ensure_plan(Adj &a, uint64_t n)
 {
     RowPlan &p = a.plan;
@@ -48,19 +55,13 @@ void ensure_plan(Adj &a, uint64_t n)
     GX_CUDA(cudaMemcpyAsync(rows.data(), p.long_rows.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
     GX_CUDA(cudaStreamSynchronize(ctx().stream));
     std::sort(rows.begin(), rows.end());
-    // fetch the offsets of the long rows only (two strided gathers would need a kernel; the
-    // list is small, so copy rowptr pairs one row at a time when few, else the whole array)
+    // offsets of the long rows only: gathered on the device, one small copy back
+    GX_CUDA(cudaMemcpyAsync(p.long_rows.p, rows.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx().stream));
+    DevBuf<uint64_t> pairs(2 * nl);
+    GX_LAUNCH(k_gather_pairs, grid_for(nl, 256), 256, 0, a.rowptr.p, p.long_rows.p, (uint64_t)nl, pairs.p);
     std::vector<uint64_t> rp_pairs(2 * nl);
-    if (nl <= 64) {
-        for (size_t i = 0; i < nl; i++)
-            GX_CUDA(cudaMemcpyAsync(&rp_pairs[2 * i], a.rowptr.p + rows[i], 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx().stream));
-        GX_CUDA(cudaStreamSynchronize(ctx().stream));
-    } else {
-        std::vector<uint64_t> rp(n + 1);
-        GX_CUDA(cudaMemcpyAsync(rp.data(), a.rowptr.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx().stream));
-        GX_CUDA(cudaStreamSynchronize(ctx().stream));
-        for (size_t i = 0; i < nl; i++) { rp_pairs[2 * i] = rp[rows[i]]; rp_pairs[2 * i + 1] = rp[rows[i] + 1]; }
-    }
+    GX_CUDA(cudaMemcpyAsync(rp_pairs.data(), pairs.p, 2 * nl * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx().stream));
+    GX_CUDA(cudaStreamSynchronize(ctx().stream));
     std::vector<uint32_t> first(nl + 1), crow;
     std::vector<uint64_t> cbeg;
     for (size_t i = 0; i < nl; i++) {
@@ -72,7 +73,6 @@ void ensure_plan(Adj &a, uint64_t n)
     p.chunk_row.alloc(p.n_chunks);
     p.chunk_begin.alloc(p.n_chunks);
     cudaStream_t s = ctx().stream;
-    GX_CUDA(cudaMemcpyAsync(p.long_rows.p, rows.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     GX_CUDA(cudaMemcpyAsync(p.long_first_chunk.p, first.data(), (nl + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     GX_CUDA(cudaMemcpyAsync(p.chunk_row.p, crow.data(), p.n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     GX_CUDA(cudaMemcpyAsync(p.chunk_begin.p, cbeg.data(), p.n_chunks * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
