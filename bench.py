@@ -25,6 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("GX_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout (one JSON line)
 
 PR_DAMPING, PR_ITERS = 0.85, 10
 BASE_SCALE, EDGEFACTOR = 22, 16
@@ -277,6 +278,7 @@ def run_gpu(args):
            "steps": e2e_steps}
 
     if rank != 0:
+        shutdown(dist)
         return
     # ---- roofline of the dominant kernel -------------------------------------------------------
     pr_iter_bytes = 4 * m + 8 * (n + 1) + 28 * n            # SURVEY.md 8(d), per PageRank iteration
@@ -314,7 +316,9 @@ def run_gpu(args):
         "config": {"workload": f"BFS + PageRank(d=0.85, {PR_ITERS} it) on directed Graph500 RMAT scale-{scale} ef={EDGEFACTOR}",
                    "vertices": n, "edges": m, "bfs_source": "max out-degree vertex",
                    "l2_policy": "inputs larger than L2 (adjacency 2 x 4m bytes >> 126 MB), no flush",
-                   "partition": "single GPU" if world == 1 else f"1-D row blocks over {world} ranks"},
+                   "partition": "single GPU" if world == 1 else
+                   f"adjacency replicated, rows split into {world} nnz-balanced blocks, per-vertex state "
+                   "all-gathered / reduced with NCCL every level / iteration"},
         "per_algorithm": {
             "bfs": {"evps": ev / (kb / args.steps * 1e-3), "kernel_ms": kb / args.steps, "levels": bfs_levels,
                     "edges_inspected": bfs_inspected, "algorithmic_bytes": bytes_b,
@@ -326,6 +330,15 @@ def run_gpu(args):
     }
     print(json.dumps(line), flush=True)
     g.free()
+    shutdown(dist)
+
+
+def shutdown(dist):
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    capi.comm_destroy()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

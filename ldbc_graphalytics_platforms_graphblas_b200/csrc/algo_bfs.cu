@@ -127,13 +127,14 @@ __global__ void k_bfs_bitmaps(const int32_t *__restrict__ level, uint64_t n, int
 
 __global__ void __launch_bounds__(256)
 k_bfs_pull(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
-           const uint64_t *__restrict__ out_rowptr, uint64_t n, const uint32_t *__restrict__ front,
-           uint32_t *__restrict__ visited, uint32_t *__restrict__ next, int32_t *__restrict__ level, int32_t depth,
-           BfsCounters *__restrict__ cnt)
+           const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1,
+           const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+           int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
 {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // [v0, v1) is this rank's row block; v0 is a multiple of 32, so a warp still owns whole words
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t nround = (n + 31) & ~31ull;
+    const uint64_t nround = (v1 + 31) & ~31ull;
     unsigned long long nf = 0, mf = 0, scanned = 0;
     for (; v < nround; v += stride) {
         const uint32_t vis = visited[v >> 5];
@@ -191,6 +192,35 @@ k_bfs_pull_long(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restri
             }
         }
     }
+}
+
+// Multi-GPU pull: after the owners' bitmap words were all-gathered, every rank applies the words
+// it does not own to its replica of level/visited and recounts the new frontier (vertices and
+// out-edges) over all words, so that all ranks take the same direction decision.
+__global__ void k_bfs_merge(const uint32_t *__restrict__ next, uint32_t *__restrict__ visited, int32_t *__restrict__ level,
+                            const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t w0, uint64_t w1, int32_t depth,
+                            BfsCounters *__restrict__ cnt)
+{
+    const uint64_t words = (n + 31) / 32;
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long nf = 0, mf = 0;
+    for (; w < words; w += stride) {
+        uint32_t bits = next[w];
+        if (!bits) continue;
+        const bool remote = w < w0 || w >= w1;
+        if (remote) visited[w] |= bits;
+        while (bits) {
+            const uint32_t v = (uint32_t)(w * 32) + (uint32_t)(__ffs(bits) - 1);
+            bits &= bits - 1;
+            if (remote) level[v] = depth;
+            nf++;
+            mf += out_rowptr[v + 1] - out_rowptr[v];
+        }
+    }
+    nf = warp_sum(nf);
+    mf = warp_sum(mf);
+    if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
 }
 
 // queue of the vertices with level == cur (pull -> push switch)
@@ -281,12 +311,20 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
                     inspected += mf;
                 } else {
                     if (!have_bitmaps) GX_LAUNCH(k_bfs_bitmaps, grid_persistent(8), 256, 0, level.p, n, depth - 1, front, bm_vis.p);
-                    GX_LAUNCH(k_bfs_pull, grid_persistent(8), 256, 0, in.rowptr.p, in.col.p, g->out.rowptr.p, n, front, bm_vis.p,
-                              next, level.p, depth, cnt.p);
+                    // pull levels are split by row block; push levels (tiny frontiers) run replicated
+                    const Partition &part = in.plan.part;
+                    GX_LAUNCH(k_bfs_pull, grid_persistent(8), 256, 0, in.rowptr.p, in.col.p, g->out.rowptr.p, n, part.lo, part.hi,
+                              front, bm_vis.p, next, level.p, depth, cnt.p);
                     if (in.plan.n_long)
                         GX_LAUNCH(k_bfs_pull_long, grid_for(in.plan.n_long * 32, 256), 256, 0, in.rowptr.p, in.col.p,
                                   g->out.rowptr.p, in.plan.long_rows.p, in.plan.n_long, front, bm_vis.p, next, level.p, depth,
                                   cnt.p);
+                    if (multi()) {
+                        allgatherv(next, Dt::U32, part, 32, words);
+                        cnt.zero();
+                        GX_LAUNCH(k_bfs_merge, grid_persistent(4), 256, 0, next, bm_vis.p, level.p, g->out.rowptr.p, n,
+                                  part.lo / 32, part.hi == n ? words : part.hi / 32, depth, cnt.p);
+                    }
                     uint32_t *t = front; front = next; next = t;
                     have_bitmaps = true;
                     have_queue = false;

@@ -31,6 +31,7 @@ constexpr uint32_t SCAN_CHUNK = 4096; // global table slots per CTA in the arg-m
 
 struct CdlpPlan {
     bool built = false;
+    Partition part; // row blocks balanced by entries (out + in)
     uint64_t nS = 0, nM = 0, nL = 0, n_ins = 0, n_scan = 0, slots = 0;
     DevBuf<uint32_t> listS, listM, listL;
     DevBuf<uint64_t> tab_off;      // nL + 1: first slot of each L row's table
@@ -49,13 +50,13 @@ __device__ __forceinline__ uint32_t hash32(uint32_t h)
     return h;
 }
 
-__global__ void k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t n,
+__global__ void k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t v0, uint64_t v1,
                            uint32_t *__restrict__ listS, uint32_t *__restrict__ listM, uint32_t *__restrict__ listL,
                            unsigned long long *__restrict__ counts, int write)
 {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; v < n; v += stride) {
+    for (; v < v1; v += stride) {
         uint64_t d = rp0[v + 1] - rp0[v];
         if (rp1) d += rp1[v + 1] - rp1[v];
         if (d == 0) continue;
@@ -236,10 +237,12 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
     const uint64_t n = g->n;
     const uint64_t *rp0 = g->out.rowptr.p;
     const uint64_t *rp1 = g->directed ? g->in.rowptr.p : nullptr;
+    p->part = make_partition(rp0, rp1, n);
+    const uint64_t v0 = p->part.lo, v1 = p->part.hi;
     DevBuf<unsigned long long> counts(3);
     counts.zero();
     DevBuf<uint32_t> dummy(1);
-    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, n, dummy.p, dummy.p, dummy.p, counts.p, 0);
+    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, dummy.p, dummy.p, dummy.p, counts.p, 0);
     unsigned long long h[3];
     read_back(h, counts.p, sizeof(h));
     p->nS = h[0]; p->nM = h[1]; p->nL = h[2];
@@ -247,7 +250,7 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
     p->listM.alloc(p->nM ? p->nM : 1);
     p->listL.alloc(p->nL ? p->nL : 1);
     counts.zero();
-    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, n, p->listS.p, p->listM.p, p->listL.p, counts.p, 1);
+    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, p->listS.p, p->listM.p, p->listL.p, counts.p, 1);
     if (p->nL) {
         std::vector<uint32_t> L(p->nL);
         std::vector<uint64_t> h0(n + 1), h1;
@@ -345,6 +348,10 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                     GX_LAUNCH((k_cdlp_rows<32, 1024>), grid_persistent(3), 256, SMEM_M, p.listM.p, p.nM, rp0, col0, rp1, col1, cur, nxt, changed.p);
                 if (p.nS)
                     GX_LAUNCH((k_cdlp_rows<8, 128>), grid_persistent(6), 256, SMEM_S, p.listS.p, p.nS, rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (multi()) {
+                    allgatherv(nxt, Dt::U32, p.part);       // owners publish their new labels
+                    allreduce(changed.p, 1, Dt::I32, Red::Max);
+                }
                 uint32_t *t = cur; cur = nxt; nxt = t;
                 iters++;
                 int h = 0;

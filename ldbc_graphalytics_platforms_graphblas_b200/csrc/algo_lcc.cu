@@ -24,12 +24,13 @@ constexpr uint32_t IDMASK = ~LCC_MULT_BIT;
 
 __global__ void __launch_bounds__(256)
 k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ orow,
-            uint64_t om, unsigned long long *__restrict__ num)
+            uint64_t e0, uint64_t om, unsigned long long *__restrict__ num)
 {
+    // oriented entries [e0, om) are this rank's share
     const unsigned sub = threadIdx.x & (LCC_G - 1);
-    uint64_t gi = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LCC_G;
+    uint64_t gi = e0 + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LCC_G;
     const uint64_t ngrp = ((uint64_t)gridDim.x * blockDim.x) / LCC_G;
-    const uint64_t trips = (om + ngrp - 1) / ngrp;
+    const uint64_t trips = (om - e0 + ngrp - 1) / ngrp;
     for (uint64_t t = 0; t < trips; t++, gi += ngrp) {
         unsigned long long su = 0, sv = 0;
         uint32_t u = 0, v = 0;
@@ -107,8 +108,11 @@ extern "C" int gx_lcc(gx_graph *g, double *lcc_host)
         {
             PhaseTimer tk(&c.timing.kernel_ms);
             num.zero();
-            if (g->om)
-                GX_LAUNCH(k_lcc_count, grid_persistent(8), 256, 0, g->orowptr.p, g->ocol.p, g->orow.p, g->om, num.p);
+            // the oriented entry list is split evenly over the ranks; corner counts are summed
+            const Partition part = make_even_partition(g->om);
+            if (part.hi > part.lo)
+                GX_LAUNCH(k_lcc_count, grid_persistent(8), 256, 0, g->orowptr.p, g->ocol.p, g->orow.p, part.lo, part.hi, num.p);
+            allreduce(num.p, n, Dt::U64, Red::Sum);
             GX_LAUNCH(k_lcc_final, grid_persistent(8), 256, 0, num.p, g->udeg.p, n, g->res_f64.p);
         }
         c.timing.iterations = 1;

@@ -20,7 +20,7 @@ namespace gx {
 
 constexpr int PR_G = 8; // lanes per short row
 
-__global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, double damping,
+__global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1, double damping,
                           double *__restrict__ d, double *__restrict__ w, double *__restrict__ sink_part)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,7 +29,8 @@ __global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, d
     double sink = 0.0;
     for (; v < n; v += stride) {
         uint64_t od = out_rowptr[v + 1] - out_rowptr[v];
-        if (od == 0) { d[v] = 0.0; w[v] = 0.0; sink += r0; }
+        // d and w0 are replicated on every rank; the sink mass is counted for owned rows only
+        if (od == 0) { d[v] = 0.0; w[v] = 0.0; if (v >= v0 && v < v1) sink += r0; }
         else { double dv = (double)od / damping; d[v] = dv; w[v] = r0 / dv; }
     }
     __shared__ double red[32];
@@ -43,9 +44,8 @@ __global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, d
     }
 }
 
-// tele = teleport + damping * (sum of sink partials) / n ; one CTA, fixed order
-__global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts, double teleport, double damping,
-                          double n, double *__restrict__ tele)
+// sum of the per-CTA sink partials; one CTA, fixed order (all-reduced across ranks afterwards)
+__global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts, double *__restrict__ sink_sum)
 {
     __shared__ double red[32];
     double s = 0.0;
@@ -56,7 +56,7 @@ __global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts,
     if (threadIdx.x < 32) {
         double x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
         x = warp_sum(x);
-        if (threadIdx.x == 0) *tele = teleport + damping * x / n;
+        if (threadIdx.x == 0) *sink_sum = x;
     }
 }
 
@@ -70,20 +70,22 @@ __device__ __forceinline__ void pr_epilogue(uint64_t v, double s, double tele, c
     if (rank) rank[v] = r;
 }
 
+struct PrScalars { double teleport, damping, n; };
+
 __global__ void __launch_bounds__(256)
-k_pr_short(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n,
-           const double *__restrict__ w, const double *__restrict__ d, const double *__restrict__ tele_p,
+k_pr_short(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t v0, uint64_t v1,
+           const double *__restrict__ w, const double *__restrict__ d, const double *__restrict__ sink_sum, PrScalars sc,
            double *__restrict__ w_new, double *__restrict__ rank, double *__restrict__ sink_part)
 {
-    const double tele = *tele_p;
+    const double tele = sc.teleport + sc.damping * *sink_sum / sc.n;
     const unsigned sub = threadIdx.x & (PR_G - 1);
-    uint64_t grp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / PR_G;
+    uint64_t grp = v0 + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / PR_G;
     const uint64_t ngrp = ((uint64_t)gridDim.x * blockDim.x) / PR_G;
     double sink = 0.0;
-    // every lane of a warp runs the same number of trips (n rounded up), so the shuffles are convergent
-    const uint64_t trips = (n + ngrp - 1) / ngrp;
+    // every lane of a warp runs the same number of trips, so the shuffles are convergent
+    const uint64_t trips = (v1 - v0 + ngrp - 1) / ngrp;
     for (uint64_t t = 0; t < trips; t++, grp += ngrp) {
-        const bool live = grp < n;
+        const bool live = grp < v1;
         uint64_t a = 0, b = 0;
         if (live) { a = rowptr[grp]; b = rowptr[grp + 1]; }
         const bool is_short = live && (b - a) <= ROW_SPLIT;
@@ -134,10 +136,10 @@ k_pr_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col
 // one warp per long row
 __global__ void __launch_bounds__(256)
 k_pr_long(const uint32_t *__restrict__ long_rows, const uint32_t *__restrict__ first_chunk, uint64_t n_long,
-          const double *__restrict__ partial, const double *__restrict__ d, const double *__restrict__ tele_p,
-          double *__restrict__ w_new, double *__restrict__ rank, double *__restrict__ sink_part)
+          const double *__restrict__ partial, const double *__restrict__ d, const double *__restrict__ sink_sum,
+          PrScalars sc, double *__restrict__ w_new, double *__restrict__ rank, double *__restrict__ sink_part)
 {
-    const double tele = *tele_p;
+    const double tele = sc.teleport + sc.damping * *sink_sum / sc.n;
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double sink = 0.0;
     if (wid < n_long) {
@@ -186,8 +188,9 @@ extern "C" int gx_pagerank(gx_graph *g, double damping_in, int iters, double *ra
             ensure_plan(in, n);
         }
         const RowPlan &plan = in.plan;
+        const uint64_t v0 = plan.part.lo, v1 = plan.part.hi;
         g->res_f64.alloc(n);
-        DevBuf<double> d(n), w0(n), w1(n), tele(1);
+        DevBuf<double> d(n), w0(n), w1(n), sink_sum(1);
         const unsigned g_short = grid_persistent(8);
         const unsigned g_long = plan.n_long ? grid_for(plan.n_long * 32, 256) : 0;
         const unsigned g_init = grid_persistent(4);
@@ -195,21 +198,27 @@ extern "C" int gx_pagerank(gx_graph *g, double damping_in, int iters, double *ra
         DevBuf<double> sink_part(nparts), partial(plan.n_chunks ? plan.n_chunks : 1);
         {
             PhaseTimer tk(&c.timing.kernel_ms);
-            const double teleport = (1.0 - damping) / (double)n;
+            // teleport' = (1-damping)/n + (damping/n) * sum_{sinks} r   (LAGr_PageRankGX)
+            const PrScalars sc{(1.0 - damping) / (double)n, damping, (double)n};
             sink_part.zero();
-            GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, damping, d.p, w0.p, sink_part.p);
+            GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, v0, v1, damping, d.p, w0.p, sink_part.p);
             if (iters == 0) GX_LAUNCH(k_fill_f64, grid_persistent(4), 256, 0, g->res_f64.p, n, 1.0 / (double)n);
             double *w_old = w0.p, *w_new = w1.p;
             for (int it = 0; it < iters; it++) {
-                GX_LAUNCH(k_pr_tele, 1, 256, 0, sink_part.p, nparts, teleport, damping, (double)n, tele.p);
+                GX_LAUNCH(k_pr_tele, 1, 256, 0, sink_part.p, nparts, sink_sum.p);
+                allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
                 double *rank = (it == iters - 1) ? g->res_f64.p : nullptr;
                 if (plan.n_chunks)
                     GX_LAUNCH(k_pr_chunk, (unsigned)plan.n_chunks, 256, 0, in.rowptr.p, in.col.p, plan.chunk_row.p,
                               plan.chunk_begin.p, w_old, partial.p);
-                GX_LAUNCH(k_pr_short, g_short, 256, 0, in.rowptr.p, in.col.p, n, w_old, d.p, tele.p, w_new, rank, sink_part.p);
+                GX_LAUNCH(k_pr_short, g_short, 256, 0, in.rowptr.p, in.col.p, v0, v1, w_old, d.p, sink_sum.p, sc, w_new, rank,
+                          sink_part.p);
                 if (g_long)
                     GX_LAUNCH(k_pr_long, g_long, 256, 0, plan.long_rows.p, plan.long_first_chunk.p, plan.n_long, partial.p,
-                              d.p, tele.p, w_new, rank, sink_part.p + g_short);
+                              d.p, sink_sum.p, sc, w_new, rank, sink_part.p + g_short);
+                // the ranks exchange the owned slices of the new w (and of r after the last iteration)
+                if (it + 1 < iters) allgatherv(w_new, Dt::F64, plan.part);
+                else allgatherv(rank, Dt::F64, plan.part);
                 double *t = w_old; w_old = w_new; w_new = t;
             }
         }

@@ -34,13 +34,14 @@ __global__ void k_sssp_init(unsigned long long *__restrict__ dist, uint64_t n, u
     if (blockIdx.x == 0 && threadIdx.x == 0) queue[0] = src;
 }
 
-// relax one edge; returns true when this thread must append v to the next frontier
+// relax one edge; returns true when this thread must append v to the next frontier.
+// inq == NULL (multi-GPU): the next frontier is derived from the min-reduced distances instead.
 __device__ __forceinline__ bool sssp_relax_edge(unsigned long long *dist, uint32_t *inq, uint32_t v, double nd)
 {
     const unsigned long long nb = (unsigned long long)__double_as_longlong(nd);
     if (nb >= dist[v]) return false;
     const unsigned long long old = atomicMin(&dist[v], nb);
-    if (nb >= old) return false;
+    if (nb >= old || inq == nullptr) return false;
     return atomicExch(&inq[v], 1u) == 0u;
 }
 
@@ -56,15 +57,17 @@ __device__ __forceinline__ void sssp_append(bool won, uint32_t v, uint32_t *next
 
 __global__ void __launch_bounds__(256)
 k_sssp_relax(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const double *__restrict__ w,
-             const uint32_t *__restrict__ queue, uint64_t qn, unsigned long long *__restrict__ dist,
-             uint32_t *__restrict__ inq, uint32_t *__restrict__ next_q, uint32_t *__restrict__ big_row,
-             uint64_t *__restrict__ big_begin, SsspCounters *__restrict__ cnt)
+             const uint32_t *__restrict__ queue, uint64_t qn, uint64_t v0, uint64_t v1,
+             unsigned long long *__restrict__ dist, uint32_t *__restrict__ inq, uint32_t *__restrict__ next_q,
+             uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, SsspCounters *__restrict__ cnt)
 {
+    // the frontier queue is replicated (in any order); a rank expands the vertices of its row block [v0, v1)
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long relaxed = 0;
     for (; wid < qn; wid += nw) {
         const uint32_t u = queue[wid];
+        if (u < v0 || u >= v1) continue;
         const uint64_t a = rowptr[u], b = rowptr[u + 1];
         if (b - a > SSSP_BIG) {
             const uint64_t nch = (b - a + CHUNK - 1) / CHUNK;
@@ -131,6 +134,25 @@ __global__ void k_sssp_clear(const uint32_t *__restrict__ queue, uint64_t qn, ui
     for (; i < qn; i += stride) inq[queue[i]] = 0;
 }
 
+// Multi-GPU: vertices whose min-reduced distance dropped during the round form the next frontier
+// (same set on every rank: dist and prev are replicated).
+__global__ void k_sssp_diff(const unsigned long long *__restrict__ dist, unsigned long long *__restrict__ prev, uint64_t n,
+                            uint32_t *__restrict__ next_q, SsspCounters *__restrict__ cnt)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nround = (n + 31) & ~31ull;
+    for (; v < nround; v += stride) {
+        bool ch = false;
+        if (v < n) {
+            const unsigned long long d = dist[v];
+            ch = d < prev[v];
+            if (ch) prev[v] = d;
+        }
+        sssp_append(ch, (uint32_t)v, next_q, cnt);
+    }
+}
+
 __global__ void k_sssp_out(const unsigned long long *__restrict__ dist, uint64_t n, double *__restrict__ out)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,9 +174,15 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
         Context &c = ctx();
         c.timing = gx_timing{};
         const uint64_t n = g->n, m = g->m;
+        {
+            PhaseTimer tb(&c.timing.build_ms);
+            ensure_plan(g->out, n);
+        }
+        const Partition &part = g->out.plan.part;
         g->res_f64.alloc(n);
         DevBuf<unsigned long long> dist(n);
         DevBuf<uint32_t> inq(n), q0(n), q1(n);
+        DevBuf<unsigned long long> prev(multi() ? n : 0);
         const uint64_t big_cap = m / CHUNK + m / SSSP_BIG + 16;
         DevBuf<uint32_t> big_row(big_cap);
         DevBuf<uint64_t> big_begin(big_cap);
@@ -166,13 +194,22 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
             GX_LAUNCH(k_sssp_init, grid_persistent(8), 256, 0, dist.p, n, (uint32_t)src, q0.p, inq.p);
             uint32_t *queue = q0.p, *next_q = q1.p;
             uint64_t qn = 1;
+            if (multi()) GX_CUDA(cudaMemcpyAsync(prev.p, dist.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream));
+            uint32_t *inq_p = multi() ? nullptr : inq.p;
             while (qn) {
                 cnt.zero();
-                GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, inq.p);
+                // each rank relaxes the out-edges of the frontier vertices in its row block, on its replica
+                if (!multi()) GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, inq.p);
                 GX_LAUNCH(k_sssp_relax, grid_for(qn * 32, 256), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue, qn,
-                          dist.p, inq.p, next_q, big_row.p, big_begin.p, cnt.p);
+                          part.lo, part.hi, dist.p, inq_p, next_q, big_row.p, big_begin.p, cnt.p);
                 GX_LAUNCH(k_sssp_relax_big, grid_persistent(4), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, big_row.p,
-                          big_begin.p, dist.p, inq.p, next_q, cnt.p);
+                          big_begin.p, dist.p, inq_p, next_q, cnt.p);
+                if (multi()) {
+                    // non-negative doubles order like their bit patterns: min over the replicas, then diff
+                    allreduce(dist.p, n, Dt::U64, Red::Min);
+                    GX_CUDA(cudaMemsetAsync(&cnt.p->next_count, 0, sizeof(unsigned long long), c.stream));
+                    GX_LAUNCH(k_sssp_diff, grid_persistent(8), 256, 0, dist.p, prev.p, n, next_q, cnt.p);
+                }
                 SsspCounters h;
                 read_back(&h, cnt.p, sizeof(h));
                 qn = h.next_count;

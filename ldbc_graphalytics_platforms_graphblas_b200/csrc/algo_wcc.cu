@@ -40,16 +40,16 @@ __device__ __forceinline__ bool wcc_apply(uint32_t *f, uint32_t u, uint32_t mn)
 }
 
 __global__ void __launch_bounds__(256)
-k_wcc_hook(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n,
+k_wcc_hook(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t v0, uint64_t v1,
            const uint32_t *__restrict__ gp, uint32_t *__restrict__ f, int *__restrict__ changed)
 {
     const unsigned sub = threadIdx.x & (WCC_G - 1);
-    uint64_t grp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / WCC_G;
+    uint64_t grp = v0 + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / WCC_G;
     const uint64_t ngrp = ((uint64_t)gridDim.x * blockDim.x) / WCC_G;
-    const uint64_t trips = (n + ngrp - 1) / ngrp;
+    const uint64_t trips = (v1 - v0 + ngrp - 1) / ngrp;
     bool ch = false;
     for (uint64_t t = 0; t < trips; t++, grp += ngrp) {
-        const bool live = grp < n;
+        const bool live = grp < v1;
         uint64_t a = 0, b = 0;
         if (live) { a = rowptr[grp]; b = rowptr[grp + 1]; }
         const bool is_short = live && b > a && (b - a) <= ROW_SPLIT;
@@ -89,13 +89,17 @@ k_wcc_hook_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict
     }
 }
 
-__global__ void k_wcc_shortcut(uint32_t *__restrict__ f, uint32_t *__restrict__ gp, uint64_t n, int *__restrict__ changed)
+// f_prev (multi-GPU only): parents before this iteration's hooking, so that a change brought in by
+// the min-reduction over the ranks' replicas also counts as a change.
+__global__ void k_wcc_shortcut(uint32_t *__restrict__ f, uint32_t *__restrict__ gp, const uint32_t *__restrict__ f_prev,
+                               uint64_t n, int *__restrict__ changed)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool ch = false;
     for (; v < n; v += stride) {
         const uint32_t fu = f[v];
+        if (f_prev && fu != f_prev[v]) ch = true;
         const uint32_t g = f[fu]; // new grandparent
         if (g != gp[v]) { gp[v] = g; ch = true; }
         if (g < fu) { atomicMin(&f[v], g); ch = true; }
@@ -115,7 +119,8 @@ static void wcc_hook_pass(Adj &a, uint64_t n, const uint32_t *gp, uint32_t *f, i
     const RowPlan &p = a.plan;
     if (p.n_chunks)
         GX_LAUNCH(k_wcc_hook_chunk, (unsigned)p.n_chunks, 256, 0, a.rowptr.p, a.col.p, p.chunk_row.p, p.chunk_begin.p, gp, f, changed);
-    GX_LAUNCH(k_wcc_hook, grid_persistent(8), 256, 0, a.rowptr.p, a.col.p, n, gp, f, changed);
+    GX_LAUNCH(k_wcc_hook, grid_persistent(8), 256, 0, a.rowptr.p, a.col.p, p.part.lo, p.part.hi, gp, f, changed);
+    (void)n;
 }
 
 } // namespace gx
@@ -139,7 +144,7 @@ extern "C" int gx_wcc(gx_graph *g, uint64_t *comp_host)
         }
         const uint64_t m_sym = g->directed ? 2 * g->m : g->m;
         g->res_u64.alloc(n);
-        DevBuf<uint32_t> f(n), gp(n);
+        DevBuf<uint32_t> f(n), gp(n), f_prev(multi() ? n : 0);
         DevBuf<int> changed(1);
         uint32_t iters = 0;
         {
@@ -147,9 +152,16 @@ extern "C" int gx_wcc(gx_graph *g, uint64_t *comp_host)
             GX_LAUNCH(k_wcc_init, grid_persistent(8), 256, 0, f.p, gp.p, n);
             for (;;) {
                 changed.zero();
+                if (multi()) GX_CUDA(cudaMemcpyAsync(f_prev.p, f.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
                 wcc_hook_pass(g->out, n, gp.p, f.p, changed.p);
                 if (g->directed) wcc_hook_pass(g->in, n, gp.p, f.p, changed.p);
-                GX_LAUNCH(k_wcc_shortcut, grid_persistent(8), 256, 0, f.p, gp.p, n, changed.p);
+                if (multi()) {
+                    // every rank hooked with the rows of its block on its own replica: combine by min
+                    allreduce(f.p, n, Dt::U32, Red::Min);
+                }
+                GX_LAUNCH(k_wcc_shortcut, grid_persistent(8), 256, 0, f.p, gp.p, multi() ? f_prev.p : nullptr, n, changed.p);
+                // replicas may shortcut in different orders; the ranks stop together, once nobody changed anything
+                allreduce(changed.p, 1, Dt::I32, Red::Max);
                 iters++;
                 int h = 0;
                 read_back(&h, changed.p, sizeof(h));

@@ -1,0 +1,34 @@
+// comm.cuh -- multi-GPU plumbing: one process per GPU, NCCL over NVLink.
+//
+// Sharding model: every rank keeps the whole adjacency in its own HBM
+// (RMAT-26 symmetric + FP64 weights is ~26 GB of 180 GB), the ROWS are split into contiguous
+// blocks balanced by entry count, and the dense per-vertex state is replicated: after each
+// bulk-synchronous step the owned slices are all-gathered (PR ranks, CDLP labels, BFS frontier
+// bitmap) or the replicas min/sum-reduced (WCC parents, SSSP distances, LCC counts).
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace gx {
+
+struct Partition {
+    std::vector<uint64_t> b; // nranks + 1 boundaries, b[0] = 0, b[nranks] = n, multiples of 32 in between
+    uint64_t lo = 0, hi = 0; // this rank's block [lo, hi)
+};
+
+// Row blocks balanced by entries of rp0 (+ rp1 when given); device arrays of n+1 offsets.
+Partition make_partition(const uint64_t *rp0, const uint64_t *rp1, uint64_t n);
+// Even split of [0, count) (work lists that are already balanced per item).
+Partition make_even_partition(uint64_t count, uint64_t align = 1);
+
+enum class Red { Sum, Min, Max };
+enum class Dt { U32, I32, U64, F64, U8 };
+
+inline bool multi() { return ctx().nranks > 1; }
+// in place: rank r contributes elements [p.b[r] / div, p.b[r+1] / div) of buf (div = 32 for bitmap words)
+void allgatherv(void *buf, Dt dt, const Partition &p, uint64_t div = 1, uint64_t total = 0);
+void allreduce(void *buf, uint64_t count, Dt dt, Red op);
+
+} // namespace gx

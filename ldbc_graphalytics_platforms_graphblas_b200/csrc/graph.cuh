@@ -9,6 +9,7 @@
 // halving the index width halves the dominant adjacency stream.
 #pragma once
 
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace gx {
@@ -21,7 +22,8 @@ constexpr uint32_t CHUNK = 2048;     // entries per CTA on the chunked path
 
 struct RowPlan {
     bool built = false;
-    uint64_t n_long = 0, n_chunks = 0;
+    Partition part;                    // row blocks of the ranks (whole range on one GPU)
+    uint64_t n_long = 0, n_chunks = 0; // long rows / chunks inside this rank's block
     DevBuf<uint32_t> long_rows;        // n_long, ascending vertex ids
     DevBuf<uint32_t> long_first_chunk; // n_long + 1
     DevBuf<uint32_t> chunk_row;        // n_chunks: vertex id

@@ -6,12 +6,12 @@
 
 namespace gx {
 
-__global__ void k_collect_long(const uint64_t *__restrict__ rowptr, uint64_t n, uint32_t thresh,
+__global__ void k_collect_long(const uint64_t *__restrict__ rowptr, uint64_t v0, uint64_t v1, uint32_t thresh,
                                uint32_t *__restrict__ list, unsigned long long *__restrict__ count, uint64_t cap)
 {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; v < n; v += stride) {
+    for (; v < v1; v += stride) {
         if (rowptr[v + 1] - rowptr[v] > thresh) {
             unsigned long long pos = atomicAdd(count, 1ull);
             if (pos < cap) list[pos] = (uint32_t)v;
@@ -31,12 +31,14 @@ void ensure_plan(Adj &a, uint64_t n)
     RowPlan &p = a.plan;
     if (p.built) return;
     p.n_long = p.n_chunks = 0;
+    p.part = make_partition(a.rowptr.p, nullptr, n);
     if (n == 0) { p.built = true; return; }
+    const uint64_t v0 = p.part.lo, v1 = p.part.hi;
     // at most m / ROW_SPLIT rows can be long; size the list by a first counting pass
     DevBuf<unsigned long long> cnt(1);
     cnt.zero();
     DevBuf<uint32_t> dummy(1);
-    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, n, ROW_SPLIT, dummy.p, cnt.p, (uint64_t)0);
+    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, v0, v1, ROW_SPLIT, dummy.p, cnt.p, (uint64_t)0);
     unsigned long long nl = 0;
     read_back(&nl, cnt.p, sizeof(nl));
     p.n_long = nl;
@@ -50,7 +52,7 @@ void ensure_plan(Adj &a, uint64_t n)
         return;
     }
     cnt.zero();
-    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, n, ROW_SPLIT, p.long_rows.p, cnt.p, (uint64_t)nl);
+    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, v0, v1, ROW_SPLIT, p.long_rows.p, cnt.p, (uint64_t)nl);
     std::vector<uint32_t> rows(nl);
     GX_CUDA(cudaMemcpyAsync(rows.data(), p.long_rows.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
     GX_CUDA(cudaStreamSynchronize(ctx().stream));

@@ -1,0 +1,65 @@
+"""Multi-GPU parity check, launched as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P tests/multi_gpu_check.py [scale]
+Every rank runs the six algorithms on the 1-D partitioned path; the results must be
+identical on all ranks and equal to the oracle (bit-exact for BFS/WCC/CDLP/SSSP, PR
+within 1e-6, LCC within 1e-9)."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import oracle  # noqa: E402
+from ldbc_graphalytics_platforms_graphblas_b200 import capi  # noqa: E402
+from ldbc_graphalytics_platforms_graphblas_b200.graphio import HostGraph  # noqa: E402
+
+
+def main():
+    scale = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    dist.init_process_group("gloo")
+    capi.init(local)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    capi.comm_init(rank, world, uid[0])
+    failures = []
+    for directed in (True, False):
+        g = capi.Graph.rmat(scale, directed, weighted=True)
+        src = g.max_degree_vertex()
+        res = {"bfs": g.bfs(src), "pr": g.pagerank(0.85, 10), "wcc": g.wcc(), "cdlp": g.cdlp(10), "lcc": g.lcc(),
+               "sssp": g.sssp(src)}
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(res, gathered, dst=0)
+        if rank == 0:
+            rp, ci, w = g.download()
+            n = g.n
+            T = oracle.transpose(n, rp, ci) if directed else None
+            ref = {"bfs": oracle.bfs(n, rp, ci, src), "pr": oracle.pagerank(n, rp, ci, 0.85, 10, transposed=T),
+                   "wcc": oracle.wcc(n, rp, ci, directed, transposed=T),
+                   "cdlp": oracle.cdlp(n, rp, ci, directed, 10, transposed=T),
+                   "lcc": oracle.lcc(n, rp, ci, directed, transposed=T), "sssp": oracle.sssp(n, rp, ci, w, src)}
+            for r, out in enumerate(gathered):
+                for alg in ref:
+                    if alg == "pr":
+                        ok = np.max(np.abs(out[alg] - ref[alg]) / ref[alg]) <= 1e-6
+                    elif alg == "lcc":
+                        ok = np.allclose(out[alg], ref[alg], rtol=1e-9, atol=0)
+                    else:
+                        ok = np.array_equal(out[alg], ref[alg])
+                    same = np.array_equal(out[alg], gathered[0][alg]) if alg != "pr" else np.allclose(out[alg], gathered[0][alg], rtol=1e-12)
+                    if not (ok and same):
+                        failures.append((directed, r, alg, bool(ok), bool(same)))
+        g.free()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "FAIL " + str(failures) if failures else f"OK world={world} scale={scale}", flush=True)
+    dist.barrier()
+    capi.comm_destroy()
+    dist.destroy_process_group()
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""N > 1 path.  CPU part (gloo, world_size 2): the partition rule and the
+exchange pattern (owners compute their row block, all-gather / min-reduce the
+replicated state) reproduce the oracle.  GPU part: launches
+tests/multi_gpu_check.py under torchrun when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from ldbc_graphalytics_platforms_graphblas_b200 import partition, rmat
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import oracle
+from ldbc_graphalytics_platforms_graphblas_b200 import partition, rmat
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = rmat.rmat_graph(11, directed=True, weighted=True)
+n, rp, ci = g.n, g.rowptr.astype(np.int64), g.colidx.astype(np.int64)
+trp, tci = oracle.transpose(n, g.rowptr, g.colidx)
+trp = trp.astype(np.int64); tci = tci.astype(np.int64)
+
+def allgatherv(vec, b):
+    parts = [None] * world
+    dist.all_gather_object(parts, vec[b[rank]:b[rank + 1]].copy())
+    return np.concatenate(parts)
+
+# PageRank: pull over the owned block of in-edge rows, all-gather w, all-reduce the sink mass
+b = partition.balanced_bounds(trp, world)
+lo, hi = b[rank], b[rank + 1]
+d = float(np.float32(0.85))
+outdeg = np.diff(rp)
+r = np.full(n, 1.0 / n)
+for it in range(10):
+    sink = torch.tensor([r[lo:hi][outdeg[lo:hi] == 0].sum()], dtype=torch.float64)
+    dist.all_reduce(sink)
+    w = np.where(outdeg > 0, r / np.where(outdeg > 0, outdeg / d, 1.0), 0.0)
+    tele = (1 - d) / n + d * float(sink) / n
+    mine = np.array([tele + w[tci[trp[v]:trp[v + 1]]].sum() for v in range(lo, hi)])
+    r = r.copy(); r[lo:hi] = mine
+    r = allgatherv(r, b)
+ref = oracle.pagerank(n, g.rowptr, g.colidx, 0.85, 10)
+assert np.max(np.abs(r - ref) / ref) < 1e-12, "partitioned PageRank"
+
+# WCC: hook with the owned rows on a replica, min-reduce the parents, stop together
+bo, bi = partition.balanced_bounds(rp, world), partition.balanced_bounds(trp, world)
+f = np.arange(n)
+while True:
+    before = f.copy()
+    for (ptr, idx, bb) in ((rp, ci, bo), (trp, tci, bi)):
+        for u in range(bb[rank], bb[rank + 1]):
+            nb = idx[ptr[u]:ptr[u + 1]]
+            if nb.size:
+                mn = f[f[nb]].min()
+                f[f[u]] = min(f[f[u]], mn); f[u] = min(f[u], mn)
+    t = torch.from_numpy(f.copy()); dist.all_reduce(t, op=dist.ReduceOp.MIN); f = t.numpy()
+    f = np.minimum(f, f[f])
+    ch = torch.tensor([int((f != before).any())]); dist.all_reduce(ch, op=dist.ReduceOp.MAX)
+    if not int(ch):
+        break
+assert np.array_equal(f.astype(np.uint64), oracle.wcc(n, g.rowptr, g.colidx, True)), "partitioned WCC"
+
+# SSSP: relax the owned frontier vertices on a replica, min-reduce, next frontier = what dropped
+src = rmat.max_out_degree_vertex(g)
+dist_v = np.full(n, np.inf); dist_v[src] = 0.0
+frontier = np.array([src])
+while frontier.size:
+    prev = dist_v.copy()
+    for u in frontier:
+        if bo[rank] <= u < bo[rank + 1]:
+            for e in range(rp[u], rp[u + 1]):
+                dist_v[ci[e]] = min(dist_v[ci[e]], prev[u] + g.weights[e])
+    t = torch.from_numpy(dist_v.copy()); dist.all_reduce(t, op=dist.ReduceOp.MIN); dist_v = t.numpy()
+    frontier = np.nonzero(dist_v < prev)[0]
+assert np.array_equal(dist_v, oracle.sssp(n, g.rowptr, g.colidx, g.weights, src)), "partitioned SSSP"
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_partition_rule():
+    g = rmat.rmat_graph(12, directed=True)
+    for nr in (1, 2, 3, 4, 8):
+        b = partition.balanced_bounds(g.rowptr, nr)
+        assert b[0] == 0 and b[-1] == g.n and len(b) == nr + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        assert all(x % 32 == 0 for x in b[1:-1])
+        loads = np.diff(g.rowptr.astype(np.int64)[b])
+        # balanced by entries up to one 32-row block and the heaviest row
+        slack = np.diff(g.rowptr.astype(np.int64)).max() * 33
+        assert loads.max() - loads.min() <= 2 * slack + g.nnz // nr // 4
+    assert partition.even_bounds(10, 4) == [0, 2, 5, 7, 10]
+    assert partition.even_bounds(100, 2, align=32) == [0, 32, 100]
+
+
+def test_world_size_2_gloo_exchange(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script), ROOT],
+                       capture_output=True, text=True, timeout=600, env={**os.environ, "OMP_NUM_THREADS": "2"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == 2
+
+
+@pytest.mark.gpu
+def test_multi_gpu_matches_oracle():
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    ngpu = capi.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29542",
+                        os.path.join(ROOT, "tests", "multi_gpu_check.py"), "16"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
