@@ -256,11 +256,19 @@ def run_gpu(args):
     pin_lvl = capi.PinnedArray((n,), np.int64)
     pin_rank = capi.PinnedArray((n,), np.float64)
 
+    e2e_parts = {}
+
     def e2e_step():
         h = capi.Graph.from_csr(n, pin_rp.array, pin_ci.array, None, True)   # H2D upload + validation
+        t_up = capi.last_timing()
         h.bfs(src, out=pin_lvl.array)                                           # builds A' on first use, D2H levels
+        t_b = capi.last_timing()
         h.pagerank(PR_DAMPING, PR_ITERS, out=pin_rank.array)                    # D2H ranks
+        t_p = capi.last_timing()
         h.free()
+        e2e_parts.update(upload_h2d_ms=t_up["h2d_ms"], upload_check_ms=t_up["build_ms"], transpose_ms=t_b["build_ms"],
+                         bfs_kernel_ms=t_b["kernel_ms"], bfs_d2h_ms=t_b["d2h_ms"], pr_plan_ms=t_p["build_ms"],
+                         pr_kernel_ms=t_p["kernel_ms"], pr_d2h_ms=t_p["d2h_ms"])
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
@@ -275,7 +283,7 @@ def run_gpu(args):
     e2e = {"value": 2 * ev / t_e2e, "unit": "edges+vertices/s", "ms_per_step": 1e3 * t_e2e,
            "h2d_bytes_per_step": int(8 * (n + 1) + 4 * m), "d2h_bytes_per_step": int(16 * n),
            "entry": "gx_graph_create_csr32 + gx_bfs + gx_pagerank + gx_graph_free, pinned host buffers",
-           "steps": e2e_steps}
+           "steps": e2e_steps, "breakdown_ms": {k: round(v, 3) for k, v in e2e_parts.items()}}
 
     if rank != 0:
         shutdown(dist)
@@ -284,7 +292,7 @@ def run_gpu(args):
     pr_iter_bytes = 4 * m + 8 * (n + 1) + 28 * n            # SURVEY.md 8(d), per PageRank iteration
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
     total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
-    pr_kernels = {k: v for k, v in prof.items() if k.startswith("k_pr_")}
+    pr_kernels = {k: v for k, v in prof.items() if k.startswith(("k_pr_", "k_pt_"))}
     pr_ms_per_iter = sum(v[1] for v in pr_kernels.values()) / (prof_steps * PR_ITERS)
     roof = {"bound": "hbm", "kernel": "PageRank iteration (" + "+".join(sorted(pr_kernels)) + ")",
             "achieved": pr_iter_bytes / (pr_ms_per_iter * 1e-3) / 1e9 if pr_ms_per_iter else None,

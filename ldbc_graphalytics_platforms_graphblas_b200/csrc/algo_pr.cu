@@ -5,20 +5,40 @@
 //   teleport' = (1-damping)/n + damping/n * sum_{sinks} r,   w = r ./ d,
 //   r = teleport' + A' (plus.second) w.
 //
-// Kernels per iteration (all HBM/L2-gather bound, no tensor-core work):
-//   k_pr_short  sub-warp group per row (<= ROW_SPLIT in-edges): streams col ids,
-//               gathers w[col], fused epilogue r -> w' = r/d and the sink sum
-//   k_pr_chunk  one CTA per CHUNK entries of a long row -> partial sums
-//   k_pr_long   one warp per long row: ordered sum of its partials + epilogue
-//   k_pr_tele   folds the per-CTA sink partials into next iteration's teleport
-// Sums are combined in a fixed order, so results are bit-reproducible.
-// Algorithmic bytes per iteration: 4m (col) + 8(n+1) (rowptr) + 8n (d) + 8n (w'),
-// gathers of w (8 B each, served by the 126 MB L2 while 8n fits).
+// What bounds it on B200 (profiles/r1_microbench_stream_patterns.txt): the 4-byte column ids
+// stream at 5.8 TB/s, but every entry also gathers one 8-byte w[source] at a random address of
+// an L2-resident vector, and an SM resolves one such gather per cycle: 284 G gathers/s, i.e.
+// >= 229 us per iteration for the 65 M entries of RMAT-22, 4.3x the HBM time of the stream.
+//
+// Shape of the kernel.  The entries of the rank's non-empty rows are cut into 256-entry tiles
+// regardless of row borders (RMAT hubs span hundreds of tiles, typical rows a dozen entries).
+// A warp takes a tile; lane L owns the 8 CONSECUTIVE entries [8L, 8L+8): two 16-byte column
+// loads and then 8 independent gathers per lane are in flight before anything is consumed
+// (the group-per-row shape of the first version kept ~1 in flight and was 27 % slower).  Row
+// borders inside a tile are a precomputed 256-bit mask (one bit per entry that starts a row).
+// A lane closes the rows that start and end among its 8 entries by itself; rows crossing lanes
+// are closed by a warp segmented scan of the lanes' open sums (5 shuffle steps per 256
+// entries); rows crossing tiles leave a head / tail partial per tile that k_pr_tile_fin adds in
+// tile order.  Rows without entries never enter the tiles.  Every sum has a fixed order, so
+// results are bit-reproducible.  w lives in an out-degree-sorted index space (the adjacency copy
+// used here stores pi(source)) whose hottest 24 K entries -- the source of 47 % of RMAT-22's
+// entries -- are staged in shared memory by every CTA.
+//
+// Kernels per iteration:
+//   k_pr_tiles     persistent, one 1024-thread CTA per SM: teleport' from the previous sink
+//                  partials, hot stage, warp-per-tile gather + segmented sums + fused epilogue
+//                  r -> w' = r/d and sink mass
+//   k_pr_tile_fin  thread per tile-crossing row (ordered sum of its partials) / per empty row
+//   (several GPUs: k_pr_tele + all-reduce of the sink mass, all-gather of w', k_pt_scatter)
+// Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
+#include <cub/device/device_scan.cuh>
+
+#include <cstdlib>
+
 #include "graph.cuh"
 
 namespace gx {
 
-constexpr int PR_G = 8; // lanes per short row
 
 __global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1, double damping,
                           double *__restrict__ d, double *__restrict__ w, double *__restrict__ sink_part)
@@ -45,111 +65,362 @@ __global__ void k_pr_init(const uint64_t *__restrict__ out_rowptr, uint64_t n, u
 }
 
 // sum of the per-CTA sink partials; one CTA, fixed order (all-reduced across ranks afterwards)
-__global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts, double *__restrict__ sink_sum)
+// block-wide sum of `count` doubles in a fixed order (every thread gets the result);
+// s_red needs (blockDim.x / 32) + 1 slots
+__device__ __forceinline__ double block_sum_ordered(const double *__restrict__ parts, unsigned count, double *s_red)
 {
-    __shared__ double red[32];
+    const unsigned nw = blockDim.x >> 5;
     double s = 0.0;
-    for (unsigned i = threadIdx.x; i < nparts; i += blockDim.x) s += sink_part[i];
+    for (unsigned i = threadIdx.x; i < count; i += blockDim.x) s += parts[i];
     s = warp_sum(s);
-    if (lane_id() == 0) red[threadIdx.x >> 5] = s;
+    if (lane_id() == 0) s_red[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
-        double x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        double x = threadIdx.x < nw ? s_red[threadIdx.x] : 0.0;
         x = warp_sum(x);
-        if (threadIdx.x == 0) *sink_sum = x;
+        if (threadIdx.x == 0) s_red[nw] = x;
     }
+    __syncthreads();
+    return s_red[nw];
 }
 
-__device__ __forceinline__ void pr_epilogue(uint64_t v, double s, double tele, const double *__restrict__ d,
-                                            double *__restrict__ w_new, double *__restrict__ rank, double &sink)
+// several GPUs only: this rank's sink partials folded into one scalar (all-reduced afterwards)
+__global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts, double *__restrict__ sink_sum)
 {
-    double r = tele + s;
-    double dv = d[v];
-    if (dv == 0.0) { sink += r; w_new[v] = 0.0; }
-    else w_new[v] = r / dv;
-    if (rank) rank[v] = r;
+    __shared__ double s_red[33];
+    const double x = block_sum_ordered(sink_part, nparts, s_red);
+    if (threadIdx.x == 0) *sink_sum = x;
 }
 
 struct PrScalars { double teleport, damping, n; };
 
-__global__ void __launch_bounds__(256)
-k_pr_short(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t v0, uint64_t v1,
-           const double *__restrict__ w, const double *__restrict__ d, const double *__restrict__ sink_sum, PrScalars sc,
-           double *__restrict__ w_new, double *__restrict__ rank, double *__restrict__ sink_part)
+__global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
 {
-    const double tele = sc.teleport + sc.damping * *sink_sum / sc.n;
-    const unsigned sub = threadIdx.x & (PR_G - 1);
-    uint64_t grp = v0 + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / PR_G;
-    const uint64_t ngrp = ((uint64_t)gridDim.x * blockDim.x) / PR_G;
-    double sink = 0.0;
-    // every lane of a warp runs the same number of trips, so the shuffles are convergent
-    const uint64_t trips = (v1 - v0 + ngrp - 1) / ngrp;
-    for (uint64_t t = 0; t < trips; t++, grp += ngrp) {
-        const bool live = grp < v1;
-        uint64_t a = 0, b = 0;
-        if (live) { a = rowptr[grp]; b = rowptr[grp + 1]; }
-        const bool is_short = live && (b - a) <= ROW_SPLIT;
-        double s = 0.0;
-        if (is_short) {
-#pragma unroll 4
-            for (uint64_t e = a + sub; e < b; e += PR_G) s += w[ld_stream(col + e)];
-        }
-#pragma unroll
-        for (int o = PR_G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-        if (is_short && sub == 0) pr_epilogue(grp, s, tele, d, w_new, rank, sink);
-    }
-    __shared__ double red[32];
-    sink = warp_sum(sink);
-    if (lane_id() == 0) red[threadIdx.x >> 5] = sink;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-        x = warp_sum(x);
-        if (threadIdx.x == 0) sink_part[blockIdx.x] = x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+
+constexpr int PT_TILE = 256;
+constexpr int PT_WARPS = 32;          // one 1024-thread CTA per SM (64 registers per thread)
+constexpr uint32_t PT_HOT = 24576;    // hottest entries of w staged in shared memory (192 KB)
+
+struct PrTiles {
+    uint64_t K = 0, M = 0, n_tiles = 0, n_span = 0, n_empty = 0; // non-empty rows, entries, ...
+    DevBuf<uint32_t> ne_rows;   // K: vertex of the k-th non-empty row of the block
+    DevBuf<uint64_t> ne_ptr;    // K+1: local entry offset of its first entry (ne_ptr[0] = 0, ne_ptr[K] = M)
+    DevBuf<uint32_t> pi;        // n: vertex -> index in the out-degree-sorted space w lives in
+    DevBuf<uint32_t> col;       // M: pi(source) of this rank's slice of the in-edges (16-byte aligned tiles)
+    DevBuf<uint32_t> tile_k0;   // n_tiles: non-empty row holding the tile's first entry; bit 31: that row starts there
+    DevBuf<uint32_t> mask;      // M bits (32 bytes per tile): entry starts a row (tile-first entries excluded)
+    DevBuf<uint32_t> slot_k;    // K: where row k's w' goes (pi(v) on one GPU, v on several)
+    DevBuf<uint32_t> span_k;    // n_span: non-empty rows lying in more than one tile
+    DevBuf<uint32_t> empty_rows; // n_empty
+};
+
+// row lists of [v0, v1): flag = 1 appends non-empty rows (in order, via their rank among
+// non-empty rows), flag = 0 appends empty rows (any order)
+__global__ void k_pt_mark(const uint64_t *__restrict__ rowptr, uint64_t v0, uint64_t v1, uint32_t *__restrict__ nonempty)
+{
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < v1; v += stride) nonempty[v - v0] = rowptr[v + 1] > rowptr[v] ? 1u : 0u;
+}
+
+__global__ void k_pt_fill(const uint64_t *__restrict__ rowptr, uint64_t v0, uint64_t v1, const uint32_t *__restrict__ rank_ne,
+                          uint64_t e0, uint32_t *__restrict__ ne_rows, uint64_t *__restrict__ ne_ptr,
+                          uint32_t *__restrict__ empty_rows)
+{
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < v1; v += stride) {
+        const uint64_t b = rowptr[v], e = rowptr[v + 1];
+        const uint32_t k = rank_ne[v - v0]; // number of non-empty rows before v
+        if (e > b) { ne_rows[k] = (uint32_t)v; ne_ptr[k] = b - e0; }
+        else empty_rows[(v - v0) - k] = (uint32_t)v; // rank among empty rows
     }
 }
 
-// one CTA (256 threads) per chunk of CHUNK entries
-__global__ void __launch_bounds__(256)
-k_pr_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ chunk_row,
-           const uint64_t *__restrict__ chunk_begin, const double *__restrict__ w, double *__restrict__ partial)
+__global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t *__restrict__ keys)
 {
-    const uint32_t c = blockIdx.x;
-    const uint64_t b = chunk_begin[c];
-    const uint64_t row_end = rowptr[chunk_row[c] + 1];
-    const uint64_t e_end = (b + CHUNK < row_end) ? b + CHUNK : row_end;
-    double s = 0.0;
-#pragma unroll 8
-    for (uint64_t e = b + threadIdx.x; e < e_end; e += 256) s += w[ld_stream(col + e)];
-    __shared__ double red[8];
-    s = warp_sum(s);
-    if (lane_id() == 0) red[threadIdx.x >> 5] = s;
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) {
+        const uint64_t od = out_rowptr[v + 1] - out_rowptr[v];
+        const uint64_t inv = 0xFFFFFFFFull - (od > 0xFFFFFFFFull ? 0xFFFFFFFFull : od); // descending out-degree
+        keys[v] = (inv << 32) | v;                                                       // ties: ascending id
+    }
+}
+
+__global__ void k_pt_make_pi(const uint64_t *__restrict__ sorted_keys, uint64_t n, uint32_t *__restrict__ pi)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) pi[(uint32_t)sorted_keys[i]] = (uint32_t)i;
+}
+
+__global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pi, uint64_t count,
+                                   uint32_t *__restrict__ out)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < count; e += stride) out[e] = pi[col[e]];
+}
+
+// w0 in the degree-sorted space (replicated on every rank)
+__global__ void k_pt_scatter(const double *__restrict__ w_nat, const uint32_t *__restrict__ pi, uint64_t n,
+                             double *__restrict__ w_perm)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) w_perm[pi[v]] = w_nat[v];
+}
+
+__device__ __forceinline__ void pt_epilogue(uint32_t v, double s, double tele, const double *__restrict__ d,
+                                            const uint32_t *__restrict__ pi, double *__restrict__ w_new,
+                                            double *__restrict__ rank, double &sink)
+{
+    const double r = tele + s;
+    const double dv = d[v];
+    const uint32_t slot = pi ? pi[v] : v; // one GPU: straight into the degree-sorted space
+    if (dv == 0.0) { sink += r; w_new[slot] = 0.0; }
+    else w_new[slot] = r / dv;
+    if (rank) rank[v] = r;
+}
+
+__global__ void k_pt_tile_k0(const uint64_t *__restrict__ ne_ptr, uint64_t K, uint64_t n_tiles, uint32_t *__restrict__ tile_k0)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; t < n_tiles; t += stride) {
+        const uint64_t B = t * PT_TILE;
+        uint64_t lo = 0, hi = K; // largest k with ne_ptr[k] <= B
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (ne_ptr[mid] <= B) lo = mid; else hi = mid;
+        }
+        tile_k0[t] = (uint32_t)lo | (ne_ptr[lo] == B ? 0x80000000u : 0u);
+    }
+}
+
+// one bit per entry that starts a row, except entries that open a tile (those are tile_k0's bit 31)
+__global__ void k_pt_mask(const uint64_t *__restrict__ ne_ptr, uint64_t K, uint32_t *__restrict__ mask)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; k < K; k += stride) {
+        const uint64_t pos = ne_ptr[k];
+        if (pos % PT_TILE) atomicOr(&mask[pos >> 5], 1u << (pos & 31));
+    }
+}
+
+__global__ void k_pt_slots(const uint32_t *__restrict__ ne_rows, const uint32_t *__restrict__ pi, uint64_t K,
+                           uint32_t *__restrict__ slot_k)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; k < K; k += stride) slot_k[k] = pi ? pi[ne_rows[k]] : ne_rows[k];
+}
+
+// per call: d in non-empty-row order, so that a tile's epilogue operands are indexed by k
+__global__ void k_pt_gather_d(const double *__restrict__ d, const uint32_t *__restrict__ ne_rows, uint64_t K,
+                              double *__restrict__ d_k)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; k < K; k += stride) d_k[k] = d[ne_rows[k]];
+}
+
+// epilogue of non-empty row k: r = teleport' + s, w' = r / d, sink mass
+__device__ __forceinline__ void pt_close(uint32_t k, double s, double tele, const double *__restrict__ d_k,
+                                         const uint32_t *__restrict__ slot_k, const uint32_t *__restrict__ ne_rows,
+                                         double *__restrict__ w_new, double *__restrict__ rank, double &sink)
+{
+    const double r = tele + s;
+    const double dv = d_k[k];
+    const uint32_t slot = slot_k[k];
+    if (dv == 0.0) { sink += r; w_new[slot] = 0.0; }
+    else w_new[slot] = r / dv;
+    if (rank) rank[ne_rows[k]] = r;
+}
+
+__global__ void k_pt_collect_span(const uint64_t *__restrict__ ne_ptr, uint64_t K, uint32_t *__restrict__ list,
+                                  unsigned long long *__restrict__ count, uint64_t cap)
+{
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; k < K; k += stride) {
+        if (ne_ptr[k] / PT_TILE != (ne_ptr[k + 1] - 1) / PT_TILE) {
+            const unsigned long long pos = atomicAdd(count, 1ull);
+            if (pos < cap) list[pos] = (uint32_t)k;
+        }
+    }
+}
+
+struct PtArgs {
+    const uint32_t *col;
+    const uint64_t *ne_ptr;
+    const uint32_t *ne_rows;
+    const uint32_t *tile_k0;
+    const uint8_t *mask;    // 32 bytes per tile
+    const uint32_t *slot_k;
+    const double *d_k;
+    const double *w;        // degree-sorted space
+    const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
+    unsigned n_sink_in;
+    double *tele_out;
+    double *w_new;
+    double *rank;
+    double *head_part;
+    double *tail_part;
+    double *sink_out;
+    uint64_t K, M, n_tiles;
+    uint32_t hot;
+    PrScalars sc;
+};
+
+__global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
+{
+    extern __shared__ double s_hot[];
+    __shared__ double s_red[PT_WARPS + 1];
+    // teleport' = (1-damping)/n + damping * sum_{sinks} r / n; every CTA adds the partials in the same order
+    const double tele = a.sc.teleport + a.sc.damping * block_sum_ordered(a.sink_in, a.n_sink_in, s_red) / a.sc.n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.tele_out = tele;
+    // the hottest sources (highest out-degree) are read from shared memory instead of through L1/L2
+    for (uint32_t i = threadIdx.x; i < a.hot; i += PT_WARPS * 32) s_hot[i] = a.w[i];
+    __syncthreads();
+    const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+    const uint64_t nwarp = (uint64_t)gridDim.x * PT_WARPS;
+    double sink = 0.0;
+    for (uint64_t t = (uint64_t)blockIdx.x * PT_WARPS + wib; t < a.n_tiles; t += nwarp) {
+        const uint64_t B = t * PT_TILE;
+        const uint64_t E = (B + PT_TILE < a.M) ? B + PT_TILE : a.M;
+        // ---- everything the tile needs is requested at once: first row, row-start bits, column ids
+        const uint32_t kk = a.tile_k0[t];
+        const uint32_t kk_next = (t + 1 < a.n_tiles) ? a.tile_k0[t + 1] : 0x80000000u;
+        const uint32_t flags = a.mask[t * 32 + lane]; // bit i: a row starts at entry 8*lane+i
+        const uint64_t p0 = B + 8ull * lane;
+        uint32_t idx[8];
+        {
+            uint4 x, y;
+            if (p0 + 8 <= E) {
+                x = ld_stream4((const uint4 *)(a.col + p0));
+                y = ld_stream4((const uint4 *)(a.col + p0 + 4));
+            } else {
+                uint32_t tmp[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) tmp[i] = (p0 + i < E) ? ld_stream(a.col + p0 + i) : 0u;
+                x = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
+                y = make_uint4(tmp[4], tmp[5], tmp[6], tmp[7]);
+            }
+            idx[0] = x.x; idx[1] = x.y; idx[2] = x.z; idx[3] = x.w; idx[4] = y.x; idx[5] = y.y; idx[6] = y.z; idx[7] = y.w;
+        }
+        const uint32_t k0 = kk & 0x7FFFFFFFu;
+        const bool k0_starts_here = (kk >> 31) != 0;   // otherwise row k0 began in an earlier tile
+        const bool ends_here = (kk_next >> 31) != 0;   // a row starts right after this tile (or the block ends)
+        // ---- the gathers: 8 independent ones per lane
+        double val[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) val[i] = (p0 + i >= E) ? 0.0 : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
+        // rows starting before this lane's first entry (exclusive prefix of the per-lane counts)
+        const uint32_t cnt = __popc(flags);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL, incl, dlt);
+            if (lane >= (unsigned)dlt) incl += up;
+        }
+        const uint32_t before = incl - cnt;
+        const uint32_t total_starts = __shfl_sync(FULL, incl, 31);
+        // ---- rows that end inside the lane: one trip per row start (a tile has ~10, a lane 0..2), so
+        // the epilogue code runs a couple of times per tile instead of once per entry position
+        uint32_t kcur = k0 + before; // row the lane's first entry belongs to
+        uint32_t f = flags, i0 = 0;
+        double head = 0.0;
+        bool seen = false;
+        while (__any_sync(FULL, f != 0)) {
+            if (f) {
+                const uint32_t i = __ffs(f) - 1;
+                f &= f - 1;
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if ((uint32_t)j >= i0 && (uint32_t)j < i) s += val[j];
+                if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
+                else pt_close(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                kcur++;
+                i0 = i;
+            }
+        }
+        double acc = 0.0; // open sum at the end of the lane
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if ((uint32_t)j >= i0) acc += val[j];
+        // ---- rows crossing lanes: segmented inclusive scan of the lanes' open sums
+        double sv = acc;
+        bool sf = seen;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const double pv = __shfl_up_sync(FULL, sv, dlt);
+            const int pf = __shfl_up_sync(FULL, (int)sf, dlt);
+            if (lane >= (unsigned)dlt) { if (!sf) sv += pv; sf = sf || pf; }
+        }
+        double carry = __shfl_up_sync(FULL, sv, 1);
+        if (lane == 0) carry = 0.0;
+        if (seen) {
+            // the row running into this lane ends at the lane's first row start
+            const double tot = carry + head;
+            if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
+            else pt_close(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+        }
+        if (lane == 31) {
+            // the row still open at the end of the tile
+            const uint32_t klast = k0 + total_starts;
+            const bool began_here = total_starts > 0 || k0_starts_here;
+            if (ends_here) {
+                if (began_here) pt_close(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                else a.head_part[t] = sv;
+            } else {
+                if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
+            }
+        }
+    }
+    __syncthreads();
+    sink = warp_sum(sink);
+    if (lane == 0) s_red[wib] = sink;
     __syncthreads();
     if (threadIdx.x == 0) {
         double x = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) x += red[i];
-        partial[c] = x;
+        for (int i = 0; i < PT_WARPS; i++) x += s_red[i];
+        a.sink_out[blockIdx.x] = x;
     }
 }
 
-// one warp per long row
+// rows crossing tile borders (tail of the first tile + heads of the next ones, added in tile
+// order) and rows without entries; one thread each -- the loads of a row are independent
 __global__ void __launch_bounds__(256)
-k_pr_long(const uint32_t *__restrict__ long_rows, const uint32_t *__restrict__ first_chunk, uint64_t n_long,
-          const double *__restrict__ partial, const double *__restrict__ d, const double *__restrict__ sink_sum,
-          PrScalars sc, double *__restrict__ w_new, double *__restrict__ rank, double *__restrict__ sink_part)
+k_pr_tile_fin(const uint64_t *__restrict__ ne_ptr, const uint32_t *__restrict__ ne_rows, const uint32_t *__restrict__ span_k,
+              uint64_t n_span, const uint32_t *__restrict__ empty_rows, uint64_t n_empty, const double *__restrict__ head_part,
+              const double *__restrict__ tail_part, const double *__restrict__ d, const uint32_t *__restrict__ pi,
+              const double *__restrict__ tele_p, double *__restrict__ w_new, double *__restrict__ rank,
+              double *__restrict__ sink_part)
 {
-    const double tele = sc.teleport + sc.damping * *sink_sum / sc.n;
-    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const double tele = *tele_p;
     double sink = 0.0;
-    if (wid < n_long) {
-        uint32_t c0 = first_chunk[wid], c1 = first_chunk[wid + 1];
-        double s = 0.0;
-        for (uint32_t c = c0 + lane_id(); c < c1; c += 32) s += partial[c];
-        s = warp_sum(s);
-        if (lane_id() == 0) pr_epilogue(long_rows[wid], s, tele, d, w_new, rank, sink);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one row per thread
+    if (i < n_span) {
+        const uint32_t k = span_k[i];
+        const uint64_t t0 = ne_ptr[k] / PT_TILE, t1 = (ne_ptr[k + 1] - 1) / PT_TILE;
+        double s = tail_part[t0];
+#pragma unroll 4
+        for (uint64_t t = t0 + 1; t <= t1; t++) s += head_part[t];
+        pt_epilogue(ne_rows[k], s, tele, d, pi, w_new, rank, sink);
+    } else if (i - n_span < n_empty) {
+        pt_epilogue(empty_rows[i - n_span], 0.0, tele, d, pi, w_new, rank, sink);
     }
     __shared__ double red[8];
+    sink = warp_sum(sink);
     if (lane_id() == 0) red[threadIdx.x >> 5] = sink;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -159,16 +430,150 @@ k_pr_long(const uint32_t *__restrict__ long_rows, const uint32_t *__restrict__ f
     }
 }
 
-__global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
+static PrTiles *build_pr_tiles(gx_graph *g)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) p[i] = v;
+    PrTiles *pt = new PrTiles();
+    Adj &in = g->in_adj();
+    const uint64_t v0 = in.plan.part.lo, v1 = in.plan.part.hi, nv = v1 - v0;
+    uint64_t ends[2] = {0, 0};
+    read_back(&ends[0], in.rowptr.p + v0, sizeof(uint64_t));
+    read_back(&ends[1], in.rowptr.p + v1, sizeof(uint64_t));
+    const uint64_t e0 = ends[0];
+    pt->M = ends[1] - ends[0];
+    pt->n_tiles = (pt->M + PT_TILE - 1) / PT_TILE;
+    // rank of every row among the non-empty rows of the block
+    DevBuf<uint32_t> flag(nv ? nv : 1), rank_ne(nv ? nv : 1);
+    uint32_t tail[2] = {0, 0};
+    if (nv) {
+        GX_LAUNCH(k_pt_mark, grid_persistent(8), 256, 0, in.rowptr.p, v0, v1, flag.p);
+        size_t tb = 0;
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank_ne.p, (int64_t)nv, ctx().stream));
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, rank_ne.p, (int64_t)nv, ctx().stream));
+        read_back(&tail[0], rank_ne.p + (nv - 1), sizeof(uint32_t));
+        read_back(&tail[1], flag.p + (nv - 1), sizeof(uint32_t));
+    }
+    pt->K = (uint64_t)tail[0] + tail[1];
+    pt->n_empty = nv - pt->K;
+    pt->ne_rows.alloc(pt->K ? pt->K : 1);
+    pt->ne_ptr.alloc(pt->K + 1);
+    pt->empty_rows.alloc(pt->n_empty ? pt->n_empty : 1);
+    if (nv)
+        GX_LAUNCH(k_pt_fill, grid_persistent(8), 256, 0, in.rowptr.p, v0, v1, rank_ne.p, e0, pt->ne_rows.p, pt->ne_ptr.p,
+                  pt->empty_rows.p);
+    GX_CUDA(cudaMemcpyAsync(pt->ne_ptr.p + pt->K, &pt->M, sizeof(uint64_t), cudaMemcpyHostToDevice, ctx().stream));
+    GX_CUDA(cudaStreamSynchronize(ctx().stream)); // &pt->M is read by the copy
+    // out-degree order of the sources: w lives in that index space, its head goes to shared memory
+    {
+        const uint64_t n = g->n;
+        pt->pi.alloc(n);
+        DevBuf<uint64_t> keys(n);
+        GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, keys.p);
+        sort_keys64(keys, n, 64);
+        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, keys.p, n, pt->pi.p);
+    }
+    // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
+    pt->col.alloc(pt->M ? pt->M : 1);
+    if (pt->M) GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, pt->col.p);
+    pt->tile_k0.alloc(pt->n_tiles ? pt->n_tiles : 1);
+    if (pt->n_tiles)
+        GX_LAUNCH(k_pt_tile_k0, grid_for(pt->n_tiles, 256), 256, 0, pt->ne_ptr.p, pt->K, pt->n_tiles, pt->tile_k0.p);
+    pt->mask.alloc(pt->n_tiles ? pt->n_tiles * (PT_TILE / 32) : 1);
+    pt->mask.zero();
+    pt->slot_k.alloc(pt->K ? pt->K : 1);
+    if (pt->K) {
+        GX_LAUNCH(k_pt_mask, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->mask.p);
+        GX_LAUNCH(k_pt_slots, grid_persistent(8), 256, 0, pt->ne_rows.p, multi() ? (const uint32_t *)nullptr : pt->pi.p, pt->K,
+                  pt->slot_k.p);
+    }
+    DevBuf<unsigned long long> cnt(1);
+    cnt.zero();
+    DevBuf<uint32_t> dummy(1);
+    if (pt->K) GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, dummy.p, cnt.p, (uint64_t)0);
+    unsigned long long ns = 0;
+    read_back(&ns, cnt.p, sizeof(ns));
+    pt->n_span = ns;
+    pt->span_k.alloc(ns ? ns : 1);
+    if (ns) {
+        cnt.zero();
+        GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->span_k.p, cnt.p, (uint64_t)ns);
+    }
+    return pt;
+}
+
+static void pagerank_tiles(gx_graph *g, double damping, int iters)
+{
+    Context &c = ctx();
+    const uint64_t n = g->n;
+    Adj &in = g->in_adj();
+    const RowPlan &plan = in.plan;
+    const PrTiles &pt = *(PrTiles *)g->pr_cache;
+    const uint64_t v0 = plan.part.lo, v1 = plan.part.hi;
+    uint32_t hot_cap = PT_HOT;
+    if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
+    const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
+    const size_t smem = (size_t)hot * sizeof(double);
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DevBuf<double> d(n), w0(n), w1(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
+    const unsigned g_tiles = (unsigned)c.num_sms;
+    const unsigned g_fin = (pt.n_span || pt.n_empty) ? grid_for(pt.n_span + pt.n_empty, 256) : 0;
+    const unsigned g_init = grid_persistent(8);
+    const unsigned nparts = (g_tiles + g_fin > g_init) ? g_tiles + g_fin : g_init;
+    DevBuf<double> sinkA(nparts), sinkB(nparts), head_part(pt.n_tiles ? pt.n_tiles : 1), tail_part(pt.n_tiles ? pt.n_tiles : 1);
+    PhaseTimer tk(&c.timing.kernel_ms);
+    // teleport' = (1-damping)/n + damping * sum_{sinks} r / n   (LAGr_PageRankGX)
+    const PrScalars sc{(1.0 - damping) / (double)n, damping, (double)n};
+    sinkA.zero();
+    sinkB.zero();
+    GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, v0, v1, damping, d.p, w_nat.p, sinkA.p);
+    GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, w0.p);
+    if (pt.K) GX_LAUNCH(k_pt_gather_d, grid_persistent(8), 256, 0, d.p, pt.ne_rows.p, pt.K, d_k.p);
+    if (iters == 0) GX_LAUNCH(k_fill_f64, grid_persistent(4), 256, 0, g->res_f64.p, n, 1.0 / (double)n);
+    double *w_old = w0.p, *w_new = w1.p, *s_in = sinkA.p, *s_out = sinkB.p;
+    for (int it = 0; it < iters; it++) {
+        const double *sink_in = s_in;
+        unsigned n_sink_in = nparts;
+        if (multi()) {
+            // the sink mass is spread over the ranks: fold the local partials, all-reduce the scalar
+            GX_LAUNCH(k_pr_tele, 1, 256, 0, s_in, nparts, sink_sum.p);
+            allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
+            sink_in = sink_sum.p;
+            n_sink_in = 1;
+        }
+        GX_CUDA(cudaMemsetAsync(s_out, 0, nparts * sizeof(double), c.stream));
+        double *rank = (it == iters - 1) ? g->res_f64.p : nullptr;
+        PtArgs a;
+        a.col = pt.col.p; a.ne_ptr = pt.ne_ptr.p; a.ne_rows = pt.ne_rows.p; a.tile_k0 = pt.tile_k0.p;
+        a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
+        a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
+        a.w_new = multi() ? w_nat.p : w_new;
+        a.rank = rank;
+        a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
+        a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
+        GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
+        if (g_fin)
+            GX_LAUNCH(k_pr_tile_fin, g_fin, 256, 0, pt.ne_ptr.p, pt.ne_rows.p, pt.span_k.p, pt.n_span, pt.empty_rows.p, pt.n_empty,
+                      head_part.p, tail_part.p, d.p, multi() ? (const uint32_t *)nullptr : pt.pi.p, tele.p, a.w_new, rank,
+                      s_out + g_tiles);
+        if (multi()) {
+            // the ranks exchange the owned slices of the new w (of r after the last iteration)
+            if (it + 1 < iters) {
+                allgatherv(w_nat.p, Dt::F64, plan.part);
+                GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, w_new);
+            } else {
+                allgatherv(rank, Dt::F64, plan.part);
+            }
+        }
+        double *t = w_old; w_old = w_new; w_new = t;
+        t = s_in; s_in = s_out; s_out = t;
+    }
 }
 
 } // namespace gx
 
 using namespace gx;
+
+void gx_pr_cache_free(void *p) { delete (PrTiles *)p; }
 
 extern "C" int gx_pagerank(gx_graph *g, double damping_in, int iters, double *rank_host)
 {
@@ -182,46 +587,13 @@ extern "C" int gx_pagerank(gx_graph *g, double damping_in, int iters, double *ra
         if (n == 0) return;
         const double damping = (double)(float)damping_in; // LAGr_PageRankGX takes `float damping`
         ensure_in_adj(g);
-        Adj &in = g->in_adj();
         {
             PhaseTimer tb(&c.timing.build_ms);
-            ensure_plan(in, n);
+            ensure_plan(g->in_adj(), n);
+            if (!g->pr_cache) g->pr_cache = build_pr_tiles(g);
         }
-        const RowPlan &plan = in.plan;
-        const uint64_t v0 = plan.part.lo, v1 = plan.part.hi;
         g->res_f64.alloc(n);
-        DevBuf<double> d(n), w0(n), w1(n), sink_sum(1);
-        const unsigned g_short = grid_persistent(8);
-        const unsigned g_long = plan.n_long ? grid_for(plan.n_long * 32, 256) : 0;
-        const unsigned g_init = grid_persistent(4);
-        const unsigned nparts = (g_short + g_long > g_init) ? g_short + g_long : g_init;
-        DevBuf<double> sink_part(nparts), partial(plan.n_chunks ? plan.n_chunks : 1);
-        {
-            PhaseTimer tk(&c.timing.kernel_ms);
-            // teleport' = (1-damping)/n + (damping/n) * sum_{sinks} r   (LAGr_PageRankGX)
-            const PrScalars sc{(1.0 - damping) / (double)n, damping, (double)n};
-            sink_part.zero();
-            GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, v0, v1, damping, d.p, w0.p, sink_part.p);
-            if (iters == 0) GX_LAUNCH(k_fill_f64, grid_persistent(4), 256, 0, g->res_f64.p, n, 1.0 / (double)n);
-            double *w_old = w0.p, *w_new = w1.p;
-            for (int it = 0; it < iters; it++) {
-                GX_LAUNCH(k_pr_tele, 1, 256, 0, sink_part.p, nparts, sink_sum.p);
-                allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
-                double *rank = (it == iters - 1) ? g->res_f64.p : nullptr;
-                if (plan.n_chunks)
-                    GX_LAUNCH(k_pr_chunk, (unsigned)plan.n_chunks, 256, 0, in.rowptr.p, in.col.p, plan.chunk_row.p,
-                              plan.chunk_begin.p, w_old, partial.p);
-                GX_LAUNCH(k_pr_short, g_short, 256, 0, in.rowptr.p, in.col.p, v0, v1, w_old, d.p, sink_sum.p, sc, w_new, rank,
-                          sink_part.p);
-                if (g_long)
-                    GX_LAUNCH(k_pr_long, g_long, 256, 0, plan.long_rows.p, plan.long_first_chunk.p, plan.n_long, partial.p,
-                              d.p, sink_sum.p, sc, w_new, rank, sink_part.p + g_short);
-                // the ranks exchange the owned slices of the new w (and of r after the last iteration)
-                if (it + 1 < iters) allgatherv(w_new, Dt::F64, plan.part);
-                else allgatherv(rank, Dt::F64, plan.part);
-                double *t = w_old; w_old = w_new; w_new = t;
-            }
-        }
+        pagerank_tiles(g, damping, iters);
         c.timing.iterations = (uint32_t)iters;
         c.timing.edges_inspected = m * (uint64_t)iters;
         c.timing.algorithmic_bytes = (uint64_t)iters * (4 * m + 8 * (n + 1) + 28 * n);

@@ -419,9 +419,11 @@ __global__ void k_max_degree(const uint64_t *__restrict__ rowptr, uint64_t n, un
 using namespace gx;
 
 void gx_cdlp_plan_free(void *p);
+void gx_pr_cache_free(void *p);
 gx_graph::~gx_graph()
 {
     if (cdlp_plan) gx_cdlp_plan_free(cdlp_plan);
+    if (pr_cache) gx_pr_cache_free(pr_cache);
 }
 
 // ------------------------------------------------------------------------- C ABI

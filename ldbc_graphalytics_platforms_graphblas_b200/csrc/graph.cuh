@@ -67,6 +67,7 @@ struct gx_graph {
     uint64_t lcc_list_bytes = 0;      // 4 * sum over oriented edges of (d+(u) + d+(v))
 
     void *cdlp_plan = nullptr;        // gx::CdlpPlan (algo_cdlp.cu), degree bins + spill tables
+    void *pr_cache = nullptr;         // gx::PrTiles (algo_pr.cu), tiling of the in-edge entries
 
     // results of the last run of each algorithm stay on the device
     gx::DevBuf<int64_t> res_i64;
