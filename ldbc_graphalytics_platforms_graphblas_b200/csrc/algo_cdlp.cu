@@ -11,10 +11,16 @@
 // memory (the reference allocates 48 B per edge, cdlp_kernel.cu:1169).
 //
 // Rows are binned by entry count d once per graph:
-//   S  d <= 64    8-lane group per row,  128-slot open-addressing table in smem
-//   M  d <= 512   warp per row,          1024-slot table in smem
-//   L  d  > 512   CHUNK-entry pieces inserted by whole CTAs into a global table
-//                 of 2d slots, slot-parallel arg-max, per-row finalize
+//   T4..T32  d <= 4 / 8 / 16 / 32   G = 4/8/16/32 lanes per row, one label per lane, counted with a
+//                  single __match_any_sync on (group, label) -- registers only, no table
+//   M  d <= 512    warp per row,  1024-slot open-addressing table in shared memory
+//   C  d <= 4096   CTA per row,   8192-slot table in shared memory
+//   H  d  > 4096   (hubs) 4096-entry pieces: a CTA first aggregates its piece in an 8192-slot smem
+//                  table, then adds one (label, count) per DISTINCT label to the row's global
+//                  table of 2d slots; then a slot-parallel arg-max and a per-row finalize
+// Shared-memory atomics cost ~4 cycles per entry per SM, so equal labels met by one warp
+// instruction are merged first (__match_any_sync, leader lane adds the count): once labels
+// converge a row's neighbours share a few labels and most atomics disappear.
 // The arg-max key is (count << 32) | ~label, so max() picks the highest count
 // and, among equals, the smallest label -- bit-exact with the sorted-run scan.
 // Algorithmic bytes per iteration: 4 m' + 8(n+1) [x2 directed] + 4n + 4n.
@@ -26,14 +32,18 @@
 namespace gx {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t CDLP_S_MAX = 64, CDLP_M_MAX = 512;
-constexpr uint32_t SCAN_CHUNK = 4096; // global table slots per CTA in the arg-max pass
+constexpr int CDLP_BINS = 7; // T4 T8 T16 T32 M C H
+constexpr uint32_t CDLP_M_MAX = 512, CDLP_C_MAX = 4096;
+constexpr uint32_t CDLP_PIECE = 4096;  // hub entries per CTA
+constexpr uint32_t CDLP_CT = 8192;     // slots of the CTA-wide shared-memory table (64 KB)
+constexpr uint32_t SCAN_CHUNK = 8192;  // global table slots per CTA in the arg-max pass
 
 struct CdlpPlan {
     bool built = false;
     Partition part; // row blocks balanced by entries (out + in)
-    uint64_t nS = 0, nM = 0, nL = 0, n_ins = 0, n_scan = 0, slots = 0;
-    DevBuf<uint32_t> listS, listM, listL;
+    uint64_t nb[CDLP_BINS] = {0, 0, 0, 0, 0, 0, 0}; // rows per bin
+    uint64_t nL = 0, n_ins = 0, n_scan = 0, slots = 0; // L = hub rows (bin H)
+    DevBuf<uint32_t> list[CDLP_BINS - 1], listL;
     DevBuf<uint64_t> tab_off;      // nL + 1: first slot of each L row's table
     DevBuf<uint32_t> ins_row;      // insert chunks: index into listL
     DevBuf<uint8_t> ins_side;      // 0 = out adjacency, 1 = in adjacency
@@ -50,9 +60,15 @@ __device__ __forceinline__ uint32_t hash32(uint32_t h)
     return h;
 }
 
+struct CdlpLists { uint32_t *l[CDLP_BINS]; };
+
+__device__ __forceinline__ int cdlp_bin_of(uint64_t d)
+{
+    return d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : d <= CDLP_M_MAX ? 4 : d <= CDLP_C_MAX ? 5 : 6;
+}
+
 __global__ void k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t v0, uint64_t v1,
-                           uint32_t *__restrict__ listS, uint32_t *__restrict__ listM, uint32_t *__restrict__ listL,
-                           unsigned long long *__restrict__ counts, int write)
+                           CdlpLists lists, unsigned long long *__restrict__ counts, int write)
 {
     uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -60,9 +76,9 @@ __global__ void k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__r
         uint64_t d = rp0[v + 1] - rp0[v];
         if (rp1) d += rp1[v + 1] - rp1[v];
         if (d == 0) continue;
-        int b = d <= CDLP_S_MAX ? 0 : d <= CDLP_M_MAX ? 1 : 2;
-        unsigned long long pos = atomicAdd(&counts[b], 1ull);
-        if (write) (b == 0 ? listS : b == 1 ? listM : listL)[pos] = (uint32_t)v;
+        const int b = cdlp_bin_of(d);
+        const unsigned long long pos = atomicAdd(&counts[b], 1ull);
+        if (write) lists.l[b][pos] = (uint32_t)v;
     }
 }
 
@@ -73,63 +89,35 @@ __global__ void k_cdlp_init(uint32_t *__restrict__ a, uint32_t *__restrict__ b, 
     for (; v < n; v += stride) { a[v] = (uint32_t)v; b[v] = (uint32_t)v; }
 }
 
-// G lanes per row, T-slot table per group in shared memory
-template <int G, int T>
+// bins T4..T32: G lanes per row, one neighbour label per lane, no table
+template <int G>
 __global__ void __launch_bounds__(256)
-k_cdlp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
             const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
             const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, int *__restrict__ changed)
 {
-    constexpr int GROUPS = 256 / G;
-    extern __shared__ uint32_t s_tab[];
-    uint32_t *s_key = s_tab;
-    uint32_t *s_cnt = s_tab + GROUPS * T;
-    for (int i = threadIdx.x; i < GROUPS * T; i += 256) { s_key[i] = EMPTY; s_cnt[i] = 0; }
-    __syncthreads();
     const unsigned sub = threadIdx.x & (G - 1);
-    uint32_t *key = s_key + (threadIdx.x / G) * T;
-    uint32_t *cnt = s_cnt + (threadIdx.x / G) * T;
     uint64_t gi = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / G;
     const uint64_t ngrp = ((uint64_t)gridDim.x * 256) / G;
-    const uint64_t trips = (count + ngrp - 1) / ngrp;
+    const uint64_t trips = (count + ngrp - 1) / ngrp; // same for every lane: the warp-wide intrinsics stay convergent
     bool ch = false;
     for (uint64_t t = 0; t < trips; t++, gi += ngrp) {
         const bool live = gi < count;
-        uint32_t v = 0;
-        uint64_t a0 = 0, d0 = 0, a1 = 0, d = 0;
+        uint32_t v = 0, lab = 0;
+        bool have = false;
         if (live) {
             v = list[gi];
-            a0 = rp0[v]; d0 = rp0[v + 1] - a0;
-            d = d0;
+            const uint64_t a0 = rp0[v], d0 = rp0[v + 1] - a0;
+            uint64_t a1 = 0, d = d0;
             if (rp1) { a1 = rp1[v]; d += rp1[v + 1] - a1; }
+            have = sub < d;
+            if (have) lab = cur[sub < d0 ? ld_stream(col0 + a0 + sub) : ld_stream(col1 + a1 + (sub - d0))];
         }
-        // table size: smallest power of two >= 2d (>= 2), at most T
-        uint32_t teff = 2;
-        while (teff < 2 * d && teff < (uint32_t)T) teff <<= 1;
-        const uint32_t mask = teff - 1;
-        for (uint64_t k = sub; k < d; k += G) {
-            const uint32_t u = k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0));
-            const uint32_t lab = cur[u];
-            uint32_t s = hash32(lab) & mask;
-            for (;;) {
-                const uint32_t old = atomicCAS(&key[s], EMPTY, lab);
-                if (old == EMPTY || old == lab) { atomicAdd(&cnt[s], 1u); break; }
-                s = (s + 1) & mask;
-            }
-        }
-        __syncwarp();
-        unsigned long long best = 0;
-        if (live) {
-            for (uint32_t s = sub; s < teff; s += G) {
-                const uint32_t c = cnt[s];
-                if (c) {
-                    const unsigned long long kk = ((unsigned long long)c << 32) | (uint32_t)~key[s];
-                    best = kk > best ? kk : best;
-                    key[s] = EMPTY;
-                    cnt[s] = 0;
-                }
-            }
-        }
+        // lanes of one row with equal labels match each other; rows (groups) and idle lanes never do
+        const unsigned long long key = have ? (((unsigned long long)(lane_id() / G) << 32) | lab)
+                                            : ((unsigned long long)(0x100u + lane_id()) << 32);
+        const unsigned same = __match_any_sync(FULL, key);
+        unsigned long long best = have ? (((unsigned long long)__popc(same) << 32) | (uint32_t)~lab) : 0ull;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
             const unsigned long long x = __shfl_xor_sync(FULL, best, o);
@@ -140,12 +128,142 @@ k_cdlp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *_
             nxt[v] = nl;
             if (nl != cur[v]) ch = true;
         }
+    }
+    if (ch) *changed = 1;
+}
+
+// add `n` occurrences of `lab` to an open-addressing table (power-of-two size) in shared memory
+__device__ __forceinline__ void smem_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, uint32_t n)
+{
+    uint32_t s = hash32(lab) & mask;
+    for (;;) {
+        uint32_t seen = ((volatile uint32_t *)key)[s];
+        if (seen == EMPTY) seen = atomicCAS(&key[s], EMPTY, lab);
+        if (seen == EMPTY || seen == lab) { atomicAdd(&cnt[s], n); break; }
+        s = (s + 1) & mask;
+    }
+}
+
+// lanes of a warp that hold the same label elect one lane to insert it with the multiplicity
+__device__ __forceinline__ void warp_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, bool valid)
+{
+    const unsigned same = __match_any_sync(FULL, valid ? lab : EMPTY);
+    if (valid && lane_id() == (unsigned)(__ffs(same) - 1)) smem_insert(key, cnt, mask, lab, __popc(same));
+}
+
+// bin M: one warp per row, 1024-slot table per warp in shared memory
+constexpr uint32_t CDLP_WT = 1024;
+__global__ void __launch_bounds__(256)
+k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+                 const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
+                 const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, int *__restrict__ changed)
+{
+    extern __shared__ uint32_t s_tab[];
+    for (uint32_t i = threadIdx.x; i < 8 * CDLP_WT * 2; i += 256) s_tab[i] = (i < 8 * CDLP_WT) ? EMPTY : 0u;
+    __syncthreads();
+    const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+    uint32_t *key = s_tab + wib * CDLP_WT;
+    uint32_t *cnt = s_tab + 8 * CDLP_WT + wib * CDLP_WT;
+    const uint64_t nwarp = (uint64_t)gridDim.x * 8;
+    bool ch = false;
+    for (uint64_t r = (uint64_t)blockIdx.x * 8 + wib; r < count; r += nwarp) {
+        const uint32_t v = list[r];
+        const uint64_t a0 = rp0[v], d0 = rp0[v + 1] - a0;
+        uint64_t a1 = 0, d = d0;
+        if (rp1) { a1 = rp1[v]; d += rp1[v + 1] - a1; }
+        uint32_t teff = 64;
+        while (teff < 2 * d && teff < CDLP_WT) teff <<= 1;
+        const uint32_t mask = teff - 1;
+        for (uint64_t base = 0; base < d; base += 32) {
+            const uint64_t k = base + lane;
+            const bool valid = k < d;
+            uint32_t lab = EMPTY;
+            if (valid) lab = cur[k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0))];
+            warp_insert(key, cnt, mask, lab, valid);
+        }
+        __syncwarp();
+        unsigned long long best = 0;
+        for (uint32_t s = lane; s < teff; s += 32) {
+            const uint32_t c = cnt[s];
+            if (c) {
+                const unsigned long long kk = ((unsigned long long)c << 32) | (uint32_t)~key[s];
+                best = kk > best ? kk : best;
+                key[s] = EMPTY;
+                cnt[s] = 0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(FULL, best, o);
+            best = x > best ? x : best;
+        }
+        if (lane == 0) {
+            const uint32_t nl = ~(uint32_t)best;
+            nxt[v] = nl;
+            if (nl != cur[v]) ch = true;
+        }
         __syncwarp();
     }
     if (ch) *changed = 1;
 }
 
-// L rows, pass 1: one CTA per CHUNK entries, insert into the row's global table
+// bin C: one CTA per row, CDLP_CT-slot table in shared memory
+__global__ void __launch_bounds__(256)
+k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+                const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
+                const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, int *__restrict__ changed)
+{
+    extern __shared__ uint32_t s_tab[];
+    uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
+    __shared__ unsigned long long s_best[8];
+    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
+    __syncthreads();
+    for (uint64_t r = blockIdx.x; r < count; r += gridDim.x) {
+        const uint32_t v = list[r];
+        const uint64_t a0 = rp0[v], d0 = rp0[v + 1] - a0;
+        uint64_t a1 = 0, d = d0;
+        if (rp1) { a1 = rp1[v]; d += rp1[v + 1] - a1; }
+        uint32_t teff = 1024;
+        while (teff < 2 * d && teff < CDLP_CT) teff <<= 1;
+        const uint32_t mask = teff - 1;
+        for (uint64_t base = 0; base < d; base += 256) {
+            const uint64_t k = base + threadIdx.x;
+            const bool valid = k < d;
+            uint32_t lab = EMPTY;
+            if (valid) lab = cur[k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0))];
+            warp_insert(key, cnt, mask, lab, valid);
+        }
+        __syncthreads();
+        unsigned long long best = 0;
+        for (uint32_t s = threadIdx.x; s < teff; s += 256) {
+            const uint32_t c = cnt[s];
+            if (c) {
+                const unsigned long long kk = ((unsigned long long)c << 32) | (uint32_t)~key[s];
+                best = kk > best ? kk : best;
+                key[s] = EMPTY;
+                cnt[s] = 0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(FULL, best, o);
+            best = x > best ? x : best;
+        }
+        if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 1; i < 8; i++) best = s_best[i] > best ? s_best[i] : best;
+            const uint32_t nl = ~(uint32_t)best;
+            nxt[v] = nl;
+            if (nl != cur[v]) *changed = 1;
+        }
+        __syncthreads();
+    }
+}
+
+// hub rows, pass 1: one CTA per CDLP_PIECE entries.  The piece is aggregated in shared memory
+// first; only its distinct labels go to the row's global table (one atomicAdd of the count each).
 __global__ void __launch_bounds__(256)
 k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict__ ins_row,
                   const uint8_t *__restrict__ ins_side, const uint64_t *__restrict__ ins_begin,
@@ -153,6 +271,10 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
                   const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1, const uint32_t *__restrict__ cur,
                   uint32_t *__restrict__ gkeys, uint32_t *__restrict__ gcnt)
 {
+    extern __shared__ uint32_t s_tab[];
+    uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
+    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
+    __syncthreads();
     const uint32_t c = blockIdx.x;
     const uint32_t li = ins_row[c];
     const uint32_t v = listL[li];
@@ -161,16 +283,25 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
     const uint32_t *col = side ? col1 : col0;
     const uint64_t b0 = ins_begin[c];
     const uint64_t row_end = rp[v + 1];
-    const uint64_t e_end = (b0 + CHUNK < row_end) ? b0 + CHUNK : row_end;
+    const uint64_t e_end = (b0 + CDLP_PIECE < row_end) ? b0 + CDLP_PIECE : row_end;
     const uint64_t t0 = tab_off[li];
     const uint64_t tsize = tab_off[li + 1] - t0;
-#pragma unroll 4
-    for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 256) {
-        const uint32_t lab = cur[ld_stream(col + e)];
+    for (uint64_t base = b0; base < e_end; base += 256) {
+        const uint64_t e = base + threadIdx.x;
+        const bool valid = e < e_end;
+        uint32_t lab = EMPTY;
+        if (valid) lab = cur[ld_stream(col + e)];
+        warp_insert(key, cnt, CDLP_CT - 1, lab, valid);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) {
+        const uint32_t cc = cnt[i];
+        if (!cc) continue;
+        const uint32_t lab = key[i];
         uint64_t s = ((uint64_t)hash32(lab) * tsize) >> 32;
         for (;;) {
             const uint32_t old = atomicCAS(&gkeys[t0 + s], EMPTY, lab);
-            if (old == EMPTY || old == lab) { atomicAdd(&gcnt[t0 + s], 1u); break; }
+            if (old == EMPTY || old == lab) { atomicAdd(&gcnt[t0 + s], cc); break; }
             s = (s + 1 == tsize) ? 0 : s + 1;
         }
     }
@@ -188,13 +319,19 @@ k_cdlp_big_scan(const uint32_t *__restrict__ scan_row, const uint64_t *__restric
     const uint64_t t_end = tab_off[li + 1];
     const uint64_t s_end = (s0 + SCAN_CHUNK < t_end) ? s0 + SCAN_CHUNK : t_end;
     unsigned long long best = 0;
-    for (uint64_t s = s0 + threadIdx.x; s < s_end; s += 256) {
-        const uint32_t cc = __ldcg(gcnt + s);
-        if (cc) {
-            const unsigned long long kk = ((unsigned long long)cc << 32) | (uint32_t)~__ldcg(gkeys + s);
-            best = kk > best ? kk : best;
-            gkeys[s] = EMPTY;
-            gcnt[s] = 0;
+    for (uint64_t sb = s0 + threadIdx.x; sb < s_end; sb += 256 * 8) {
+        uint32_t cc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const uint64_t q = sb + (uint64_t)j * 256; cc[j] = q < s_end ? __ldcg(gcnt + q) : 0u; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (cc[j]) {
+                const uint64_t q = sb + (uint64_t)j * 256;
+                const unsigned long long kk = ((unsigned long long)cc[j] << 32) | (uint32_t)~__ldcg(gkeys + q);
+                best = kk > best ? kk : best;
+                gkeys[q] = EMPTY;
+                gcnt[q] = 0;
+            }
         }
     }
 #pragma unroll
@@ -239,18 +376,21 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
     const uint64_t *rp1 = g->directed ? g->in.rowptr.p : nullptr;
     p->part = make_partition(rp0, rp1, n);
     const uint64_t v0 = p->part.lo, v1 = p->part.hi;
-    DevBuf<unsigned long long> counts(3);
+    DevBuf<unsigned long long> counts(CDLP_BINS);
     counts.zero();
     DevBuf<uint32_t> dummy(1);
-    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, dummy.p, dummy.p, dummy.p, counts.p, 0);
-    unsigned long long h[3];
+    CdlpLists lists;
+    for (int b = 0; b < CDLP_BINS; b++) lists.l[b] = dummy.p;
+    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, lists, counts.p, 0);
+    unsigned long long h[CDLP_BINS];
     read_back(h, counts.p, sizeof(h));
-    p->nS = h[0]; p->nM = h[1]; p->nL = h[2];
-    p->listS.alloc(p->nS ? p->nS : 1);
-    p->listM.alloc(p->nM ? p->nM : 1);
+    for (int b = 0; b < CDLP_BINS; b++) p->nb[b] = h[b];
+    p->nL = h[CDLP_BINS - 1];
+    for (int b = 0; b < CDLP_BINS - 1; b++) { p->list[b].alloc(h[b] ? h[b] : 1); lists.l[b] = p->list[b].p; }
     p->listL.alloc(p->nL ? p->nL : 1);
+    lists.l[CDLP_BINS - 1] = p->listL.p;
     counts.zero();
-    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, p->listS.p, p->listM.p, p->listL.p, counts.p, 1);
+    GX_LAUNCH(k_cdlp_bin, grid_persistent(8), 256, 0, rp0, rp1, v0, v1, lists, counts.p, 1);
     if (p->nL) {
         std::vector<uint32_t> L(p->nL);
         std::vector<uint64_t> h0(n + 1), h1;
@@ -267,10 +407,10 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
         for (uint64_t i = 0; i < p->nL; i++) {
             const uint32_t v = L[i];
             uint64_t d = h0[v + 1] - h0[v];
-            for (uint64_t b = h0[v]; b < h0[v + 1]; b += CHUNK) { ins_row.push_back((uint32_t)i); ins_side.push_back(0); ins_begin.push_back(b); }
+            for (uint64_t b = h0[v]; b < h0[v + 1]; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(0); ins_begin.push_back(b); }
             if (rp1) {
                 d += h1[v + 1] - h1[v];
-                for (uint64_t b = h1[v]; b < h1[v + 1]; b += CHUNK) { ins_row.push_back((uint32_t)i); ins_side.push_back(1); ins_begin.push_back(b); }
+                for (uint64_t b = h1[v]; b < h1[v + 1]; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(1); ins_begin.push_back(b); }
             }
             tab_off[i] = off;
             for (uint64_t sb = off; sb < off + 2 * d; sb += SCAN_CHUNK) { scan_row.push_back((uint32_t)i); scan_begin.push_back(sb); }
@@ -324,9 +464,10 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
         CdlpPlan &p = *(CdlpPlan *)g->cdlp_plan;
         const uint64_t *rp0 = g->out.rowptr.p, *rp1 = g->directed ? g->in.rowptr.p : nullptr;
         const uint32_t *col0 = g->out.col.p, *col1 = g->directed ? g->in.col.p : nullptr;
-        constexpr size_t SMEM_M = (256 / 32) * 1024 * 8, SMEM_S = (256 / 8) * 128 * 8;
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_rows<32, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_M));
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_rows<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_S));
+        constexpr size_t SMEM_M = (size_t)8 * CDLP_WT * 8, SMEM_C = (size_t)CDLP_CT * 8;
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_warp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_M));
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_big_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
         g->res_u64.alloc(n);
         DevBuf<uint32_t> la(n), lb(n);
         DevBuf<int> changed(1);
@@ -338,16 +479,20 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
             for (int it = 0; it < itermax; it++) {
                 changed.zero();
                 if (p.nL) {
-                    GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, 256, 0, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
+                    GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, 256, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
                               p.tab_off.p, rp0, col0, rp1, col1, cur, p.gkeys.p, p.gcnt.p);
                     GX_LAUNCH(k_cdlp_big_scan, (unsigned)p.n_scan, 256, 0, p.scan_row.p, p.scan_begin.p, p.tab_off.p, p.gkeys.p,
                               p.gcnt.p, p.best.p);
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, changed.p);
                 }
-                if (p.nM)
-                    GX_LAUNCH((k_cdlp_rows<32, 1024>), grid_persistent(3), 256, SMEM_M, p.listM.p, p.nM, rp0, col0, rp1, col1, cur, nxt, changed.p);
-                if (p.nS)
-                    GX_LAUNCH((k_cdlp_rows<8, 128>), grid_persistent(6), 256, SMEM_S, p.listS.p, p.nS, rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[5])
+                    GX_LAUNCH(k_cdlp_cta_rows, grid_persistent(3), 256, SMEM_C, p.list[5].p, p.nb[5], rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[4])
+                    GX_LAUNCH(k_cdlp_warp_rows, grid_persistent(3), 256, SMEM_M, p.list[4].p, p.nb[4], rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[3]) GX_LAUNCH(k_cdlp_tiny<32>, grid_persistent(8), 256, 0, p.list[3].p, p.nb[3], rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[2]) GX_LAUNCH(k_cdlp_tiny<16>, grid_persistent(8), 256, 0, p.list[2].p, p.nb[2], rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[1]) GX_LAUNCH(k_cdlp_tiny<8>, grid_persistent(8), 256, 0, p.list[1].p, p.nb[1], rp0, col0, rp1, col1, cur, nxt, changed.p);
+                if (p.nb[0]) GX_LAUNCH(k_cdlp_tiny<4>, grid_persistent(8), 256, 0, p.list[0].p, p.nb[0], rp0, col0, rp1, col1, cur, nxt, changed.p);
                 if (multi()) {
                     allgatherv(nxt, Dt::U32, p.part);       // owners publish their new labels
                     allreduce(changed.p, 1, Dt::I32, Red::Max);
