@@ -114,7 +114,7 @@ struct PrTiles {
     DevBuf<uint32_t> col;       // M: pi(source) of this rank's slice of the in-edges (16-byte aligned tiles)
     DevBuf<uint32_t> tile_k0;   // n_tiles: non-empty row holding the tile's first entry; bit 31: that row starts there
     DevBuf<uint32_t> mask;      // M bits (32 bytes per tile): entry starts a row (tile-first entries excluded)
-    DevBuf<uint32_t> slot_k;    // K: where row k's w' goes (pi(v) on one GPU, v on several)
+    DevBuf<uint32_t> slot_k;    // K: pi(vertex of row k), where its w' goes
     DevBuf<uint32_t> span_k;    // n_span: non-empty rows lying in more than one tile
     DevBuf<uint32_t> empty_rows; // n_empty
 };
@@ -142,14 +142,20 @@ __global__ void k_pt_fill(const uint64_t *__restrict__ rowptr, uint64_t v0, uint
     }
 }
 
-__global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t *__restrict__ keys)
+// Sort key of the index space w lives in: owner rank first (each rank's rows then occupy one
+// contiguous segment, so the all-gather needs no re-ordering), inside a segment by descending
+// out-degree (the often-gathered entries share cache lines), ties by vertex id.
+__global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64_t n, const uint64_t *__restrict__ bounds,
+                                 int nranks, uint64_t *__restrict__ keys)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; v < n; v += stride) {
+        uint64_t owner = 0;
+        while ((int)owner + 1 < nranks && v >= bounds[owner + 1]) owner++;
         const uint64_t od = out_rowptr[v + 1] - out_rowptr[v];
-        const uint64_t inv = 0xFFFFFFFFull - (od > 0xFFFFFFFFull ? 0xFFFFFFFFull : od); // descending out-degree
-        keys[v] = (inv << 32) | v;                                                       // ties: ascending id
+        const uint64_t inv = 0xFFFFFFull - (od > 0xFFFFFFull ? 0xFFFFFFull : od);
+        keys[v] = (owner << 56) | (inv << 32) | v;
     }
 }
 
@@ -468,7 +474,10 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         const uint64_t n = g->n;
         pt->pi.alloc(n);
         DevBuf<uint64_t> keys(n);
-        GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, keys.p);
+        DevBuf<uint64_t> bounds(in.plan.part.b.size());
+        GX_CUDA(cudaMemcpyAsync(bounds.p, in.plan.part.b.data(), in.plan.part.b.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                ctx().stream));
+        GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, bounds.p, ctx().nranks, keys.p);
         sort_keys64(keys, n, 64);
         GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, keys.p, n, pt->pi.p);
     }
@@ -483,8 +492,7 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     pt->slot_k.alloc(pt->K ? pt->K : 1);
     if (pt->K) {
         GX_LAUNCH(k_pt_mask, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->mask.p);
-        GX_LAUNCH(k_pt_slots, grid_persistent(8), 256, 0, pt->ne_rows.p, multi() ? (const uint32_t *)nullptr : pt->pi.p, pt->K,
-                  pt->slot_k.p);
+        GX_LAUNCH(k_pt_slots, grid_persistent(8), 256, 0, pt->ne_rows.p, pt->pi.p, pt->K, pt->slot_k.p);
     }
     DevBuf<unsigned long long> cnt(1);
     cnt.zero();
@@ -546,24 +554,18 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.col = pt.col.p; a.ne_ptr = pt.ne_ptr.p; a.ne_rows = pt.ne_rows.p; a.tile_k0 = pt.tile_k0.p;
         a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
         a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
-        a.w_new = multi() ? w_nat.p : w_new;
+        a.w_new = w_new;
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
         GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
         if (g_fin)
             GX_LAUNCH(k_pr_tile_fin, g_fin, 256, 0, pt.ne_ptr.p, pt.ne_rows.p, pt.span_k.p, pt.n_span, pt.empty_rows.p, pt.n_empty,
-                      head_part.p, tail_part.p, d.p, multi() ? (const uint32_t *)nullptr : pt.pi.p, tele.p, a.w_new, rank,
-                      s_out + g_tiles);
-        if (multi()) {
-            // the ranks exchange the owned slices of the new w (of r after the last iteration)
-            if (it + 1 < iters) {
-                allgatherv(w_nat.p, Dt::F64, plan.part);
-                GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, w_new);
-            } else {
-                allgatherv(rank, Dt::F64, plan.part);
-            }
-        }
+                      head_part.p, tail_part.p, d.p, pt.pi.p, tele.p, w_new, rank, s_out + g_tiles);
+        // the ranks exchange their segments of the new w (their slices of r after the last iteration);
+        // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
+        if (it + 1 < iters) allgatherv(w_new, Dt::F64, plan.part);
+        else allgatherv(rank, Dt::F64, plan.part);
         double *t = w_old; w_old = w_new; w_new = t;
         t = s_in; s_in = s_out; s_out = t;
     }

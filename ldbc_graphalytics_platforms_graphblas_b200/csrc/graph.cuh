@@ -53,6 +53,8 @@ uint64_t select_flagged(const uint64_t *in, const uint8_t *flags, uint64_t count
 struct gx_graph {
     uint64_t n = 0, m = 0;
     bool directed = false, weighted = false;
+    double mean_weight = 1.0;         // of the stored FP64 values (SSSP bucket width)
+    bool have_mean_weight = false;
     gx::Adj out;          // CSR: row v = out-neighbours of v
     gx::Adj in;           // CSC: row v = in-neighbours of v (directed only, built lazily)
     bool have_in = false;
