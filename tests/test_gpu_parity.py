@@ -122,6 +122,20 @@ def test_hub_rows(capi, directed):
     check_all(capi, csr_from_edges(n, src, dst, w, directed), src=0)
 
 
+def test_lcc_every_apex_size_class(capi):
+    """A clique: oriented out-degrees run from 0 to n-1 (long and short lists meet in every
+    intersection), and the answer is known in closed form: LCC is exactly 1 everywhere."""
+    n = 3000
+    i, j = np.triu_indices(n, 1)
+    hg = csr_from_edges(n, i, j, None, directed=False)
+    g = capi.Graph.from_host(hg)
+    try:
+        out = g.lcc()
+    finally:
+        g.free()
+    assert np.array_equal(out, np.ones(n))
+
+
 def test_unreachable_hub_in_pull(capi):
     """A vertex with a long in-list that BFS never reaches is scanned by the warp-per-row pull."""
     n = 5000
