@@ -33,6 +33,7 @@
 // Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "graph.cuh"
@@ -110,7 +111,8 @@ struct PrTiles {
     uint64_t K = 0, M = 0, n_tiles = 0, n_span = 0, n_empty = 0; // non-empty rows, entries, ...
     DevBuf<uint32_t> ne_rows;   // K: vertex of the k-th non-empty row of the block
     DevBuf<uint64_t> ne_ptr;    // K+1: local entry offset of its first entry (ne_ptr[0] = 0, ne_ptr[K] = M)
-    DevBuf<uint32_t> pi;        // n: vertex -> index in the out-degree-sorted space w lives in
+    DevBuf<uint32_t> pi;        // n: vertex -> slot in the index space w lives in (see k_pt_make_pi)
+    uint64_t seg = 0, slots = 0; // slots per rank segment (equal, padded), nranks * seg
     DevBuf<uint32_t> col;       // M: pi(source) of this rank's slice of the in-edges (16-byte aligned tiles)
     DevBuf<uint32_t> tile_k0;   // n_tiles: non-empty row holding the tile's first entry; bit 31: that row starts there
     DevBuf<uint32_t> mask;      // M bits (32 bytes per tile): entry starts a row (tile-first entries excluded)
@@ -159,11 +161,18 @@ __global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64
     }
 }
 
-__global__ void k_pt_make_pi(const uint64_t *__restrict__ sorted_keys, uint64_t n, uint32_t *__restrict__ pi)
+// slot of the i-th vertex in sorted order: rank r's vertices fill the first (b[r+1] - b[r]) slots of the
+// segment [r * seg, (r+1) * seg) -- equal, padded segments, so the exchange is one plain all-gather
+__global__ void k_pt_make_pi(const uint64_t *__restrict__ sorted_keys, uint64_t n, const uint64_t *__restrict__ bounds,
+                             uint64_t seg, uint32_t *__restrict__ pi)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) pi[(uint32_t)sorted_keys[i]] = (uint32_t)i;
+    for (; i < n; i += stride) {
+        const uint64_t key = sorted_keys[i];
+        const uint64_t owner = key >> 56;
+        pi[(uint32_t)key] = (uint32_t)(owner * seg + (i - bounds[owner]));
+    }
 }
 
 __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pi, uint64_t count,
@@ -479,7 +488,12 @@ static PrTiles *build_pr_tiles(gx_graph *g)
                                 ctx().stream));
         GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, bounds.p, ctx().nranks, keys.p);
         sort_keys64(keys, n, 64);
-        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, keys.p, n, pt->pi.p);
+        uint64_t seg = 0;
+        for (int r = 0; r < ctx().nranks; r++) seg = std::max<uint64_t>(seg, in.plan.part.b[r + 1] - in.plan.part.b[r]);
+        pt->seg = (seg + 31) & ~31ull;
+        pt->slots = pt->seg * (uint64_t)ctx().nranks;
+        GX_REQUIRE(pt->slots < 0xFFFFFFFFull, "vertex slot space exceeds 32 bits");
+        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, keys.p, n, bounds.p, pt->seg, pt->pi.p);
     }
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
     pt->col.alloc(pt->M ? pt->M : 1);
@@ -522,7 +536,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
     const size_t smem = (size_t)hot * sizeof(double);
     GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DevBuf<double> d(n), w0(n), w1(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
+    DevBuf<double> d(n), w0(pt.slots), w1(pt.slots), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
+    if (multi()) { w0.zero(); w1.zero(); } // padding slots are exchanged but never gathered
     const unsigned g_tiles = (unsigned)c.num_sms;
     const unsigned g_fin = (pt.n_span || pt.n_empty) ? grid_for(pt.n_span + pt.n_empty, 256) : 0;
     const unsigned g_init = grid_persistent(8);
@@ -564,7 +579,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
                       head_part.p, tail_part.p, d.p, pt.pi.p, tele.p, w_new, rank, s_out + g_tiles);
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
-        if (it + 1 < iters) allgatherv(w_new, Dt::F64, plan.part);
+        if (it + 1 < iters) allgather_equal(w_new, Dt::F64, pt.seg);
         else allgatherv(rank, Dt::F64, plan.part);
         double *t = w_old; w_old = w_new; w_new = t;
         t = s_in; s_in = s_out; s_out = t;

@@ -97,6 +97,17 @@ void allgatherv(void *buf, Dt dt, const Partition &p, uint64_t div, uint64_t tot
     if (prof) prof_end();
 }
 
+void allgather_equal(void *buf, Dt dt, uint64_t count_per_rank)
+{
+    Context &c = ctx();
+    if (c.nranks <= 1 || count_per_rank == 0) return;
+    const bool prof = profiling();
+    if (prof) prof_begin("nccl_allgather");
+    char *mine = (char *)buf + (uint64_t)c.rank * count_per_rank * dt_size(dt);
+    GX_NCCL(ncclAllGather(mine, buf, count_per_rank, nccl_dt(dt), (ncclComm_t)c.nccl_comm, c.stream));
+    if (prof) prof_end();
+}
+
 void allreduce(void *buf, uint64_t count, Dt dt, Red op)
 {
     Context &c = ctx();

@@ -29,6 +29,8 @@ enum class Dt { U32, I32, U64, F64, U8 };
 inline bool multi() { return ctx().nranks > 1; }
 // in place: rank r contributes elements [p.b[r] / div, p.b[r+1] / div) of buf (div = 32 for bitmap words)
 void allgatherv(void *buf, Dt dt, const Partition &p, uint64_t div = 1, uint64_t total = 0);
+// in place, equal blocks: rank r contributes elements [r * count_per_rank, (r+1) * count_per_rank) of buf
+void allgather_equal(void *buf, Dt dt, uint64_t count_per_rank);
 void allreduce(void *buf, uint64_t count, Dt dt, Red op);
 
 } // namespace gx

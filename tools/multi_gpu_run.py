@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Run one algorithm on N ranks (torchrun) and print timing from rank 0.
+    python -m torch.distributed.run --nproc-per-node 8 tools/multi_gpu_run.py --algos sssp --scale 26 --undirected
+Development tool for the configs of BASELINE.json that need several GPUs."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["NCCL_DEBUG"] = "WARN"
+from ldbc_graphalytics_platforms_graphblas_b200 import capi  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--algos", default="sssp")
+    ap.add_argument("--scale", type=int, default=24)
+    ap.add_argument("--undirected", action="store_true")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    dist.init_process_group("gloo")
+    capi.init(local)
+    uid = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    capi.comm_init(rank, world, uid[0])
+    algos = args.algos.split(",")
+    t0 = time.perf_counter()
+    g = capi.Graph.rmat(args.scale, not args.undirected, weighted="sssp" in algos, want_mapping=False)
+    src = g.max_degree_vertex()
+    if rank == 0:
+        print(f"# RMAT-{args.scale}: n={g.n} nnz={g.nnz} built in {time.perf_counter() - t0:.2f}s on {world} ranks", file=sys.stderr)
+    ev = g.n + g.num_edges
+    run = {"bfs": lambda: g.bfs(src, out=False), "pr": lambda: g.pagerank(0.85, 10, out=False), "wcc": lambda: g.wcc(out=False),
+           "cdlp": lambda: g.cdlp(10, out=False), "lcc": lambda: g.lcc(out=False), "sssp": lambda: g.sssp(src, out=False)}
+    for alg in algos:
+        run[alg]()
+        best = None
+        for _ in range(args.reps):
+            dist.barrier()
+            t1 = time.perf_counter()
+            run[alg]()
+            dt = time.perf_counter() - t1
+            t = capi.last_timing()
+            if best is None or dt < best[0]:
+                best = (dt, t)
+        capi.profile(True)
+        run[alg]()
+        capi.profile(False)
+        prof = capi.profile_report()
+        if rank == 0:
+            print(json.dumps({"alg": alg, "ranks": world, "scale": args.scale, "n": g.n, "nnz": g.nnz,
+                              "wall_ms": round(best[0] * 1e3, 3), "kernel_ms": round(best[1]["kernel_ms"], 3),
+                              "evps": ev / best[0], "iterations": best[1]["iterations"],
+                              "kernels": {k: [v[0], round(v[1], 3)] for k, v in list(prof.items())[:8]}}), flush=True)
+    g.free()
+    dist.barrier()
+    capi.comm_destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
