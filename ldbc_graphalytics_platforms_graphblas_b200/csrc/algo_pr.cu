@@ -95,6 +95,23 @@ __global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts,
 
 struct PrScalars { double teleport, damping, n; };
 
+// Where a new w' value goes: this rank's copy and, on several GPUs, every peer's copy of the vector
+// (stores over NVLink peer mappings).  The exchange of w' is thereby part of the kernels that
+// compute it; the all-reduce of the sink mass that opens the next iteration is the only barrier:
+// it completes on a rank after every rank finished these kernels, i.e. after all their peer
+// stores, and a rank reuses a buffer only two iterations later.
+struct WOut {
+    double *p[MAX_PEERS];
+    int n;
+};
+
+__device__ __forceinline__ void w_store(const WOut &o, uint32_t slot, double v)
+{
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (r < o.n) o.p[r][slot] = v;
+}
+
 __global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,6 +130,9 @@ struct PrTiles {
     DevBuf<uint64_t> ne_ptr;    // K+1: local entry offset of its first entry (ne_ptr[0] = 0, ne_ptr[K] = M)
     DevBuf<uint32_t> pi;        // n: vertex -> slot in the index space w lives in (see k_pt_make_pi)
     uint64_t seg = 0, slots = 0; // slots per rank segment (equal, padded), nranks * seg
+    PeerBuf wbuf[2];             // the two copies of w (read / written in turn), mapped into all ranks
+    bool have_wbuf = false;
+    ~PrTiles() { if (have_wbuf) { peer_free(wbuf[0]); peer_free(wbuf[1]); } }
     DevBuf<uint32_t> col;       // M: pi(source) of this rank's slice of the in-edges (16-byte aligned tiles)
     DevBuf<uint32_t> tile_k0;   // n_tiles: non-empty row holding the tile's first entry; bit 31: that row starts there
     DevBuf<uint32_t> mask;      // M bits (32 bytes per tile): entry starts a row (tile-first entries excluded)
@@ -193,14 +213,14 @@ __global__ void k_pt_scatter(const double *__restrict__ w_nat, const uint32_t *_
 }
 
 __device__ __forceinline__ void pt_epilogue(uint32_t v, double s, double tele, const double *__restrict__ d,
-                                            const uint32_t *__restrict__ pi, double *__restrict__ w_new,
+                                            const uint32_t *__restrict__ pi, const WOut &w_new,
                                             double *__restrict__ rank, double &sink)
 {
     const double r = tele + s;
     const double dv = d[v];
     const uint32_t slot = pi ? pi[v] : v; // one GPU: straight into the degree-sorted space
-    if (dv == 0.0) { sink += r; w_new[slot] = 0.0; }
-    else w_new[slot] = r / dv;
+    if (dv == 0.0) sink += r;
+    w_store(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
     if (rank) rank[v] = r;
 }
 
@@ -250,13 +270,13 @@ __global__ void k_pt_gather_d(const double *__restrict__ d, const uint32_t *__re
 // epilogue of non-empty row k: r = teleport' + s, w' = r / d, sink mass
 __device__ __forceinline__ void pt_close(uint32_t k, double s, double tele, const double *__restrict__ d_k,
                                          const uint32_t *__restrict__ slot_k, const uint32_t *__restrict__ ne_rows,
-                                         double *__restrict__ w_new, double *__restrict__ rank, double &sink)
+                                         const WOut &w_new, double *__restrict__ rank, double &sink)
 {
     const double r = tele + s;
     const double dv = d_k[k];
     const uint32_t slot = slot_k[k];
-    if (dv == 0.0) { sink += r; w_new[slot] = 0.0; }
-    else w_new[slot] = r / dv;
+    if (dv == 0.0) sink += r;
+    w_store(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
     if (rank) rank[ne_rows[k]] = r;
 }
 
@@ -285,7 +305,7 @@ struct PtArgs {
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
     double *tele_out;
-    double *w_new;
+    WOut w_new;
     double *rank;
     double *head_part;
     double *tail_part;
@@ -418,7 +438,7 @@ __global__ void __launch_bounds__(256)
 k_pr_tile_fin(const uint64_t *__restrict__ ne_ptr, const uint32_t *__restrict__ ne_rows, const uint32_t *__restrict__ span_k,
               uint64_t n_span, const uint32_t *__restrict__ empty_rows, uint64_t n_empty, const double *__restrict__ head_part,
               const double *__restrict__ tail_part, const double *__restrict__ d, const uint32_t *__restrict__ pi,
-              const double *__restrict__ tele_p, double *__restrict__ w_new, double *__restrict__ rank,
+              const double *__restrict__ tele_p, const WOut w_new, double *__restrict__ rank,
               double *__restrict__ sink_part)
 {
     const double tele = *tele_p;
@@ -536,8 +556,21 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
     const size_t smem = (size_t)hot * sizeof(double);
     GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DevBuf<double> d(n), w0(pt.slots), w1(pt.slots), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
-    if (multi()) { w0.zero(); w1.zero(); } // padding slots are exchanged but never gathered
+    PrTiles &ptm = *(PrTiles *)g->pr_cache;
+    if (!ptm.have_wbuf) {
+        peer_alloc(ptm.wbuf[0], pt.slots * sizeof(double));
+        peer_alloc(ptm.wbuf[1], pt.slots * sizeof(double));
+        ptm.have_wbuf = true;
+    }
+    // fused exchange (peer stores from the kernels) unless the mapping failed or GX_PR_FUSED=0
+    const char *fe = getenv("GX_PR_FUSED");
+    const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && !(fe && fe[0] == '0');
+    DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
+    double *wv[2] = {(double *)pt.wbuf[0].local, (double *)pt.wbuf[1].local};
+    if (multi()) { // padding slots are exchanged but never gathered
+        GX_CUDA(cudaMemsetAsync(wv[0], 0, pt.slots * sizeof(double), c.stream));
+        GX_CUDA(cudaMemsetAsync(wv[1], 0, pt.slots * sizeof(double), c.stream));
+    }
     const unsigned g_tiles = (unsigned)c.num_sms;
     const unsigned g_fin = (pt.n_span || pt.n_empty) ? grid_for(pt.n_span + pt.n_empty, 256) : 0;
     const unsigned g_init = grid_persistent(8);
@@ -549,10 +582,15 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     sinkA.zero();
     sinkB.zero();
     GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, v0, v1, damping, d.p, w_nat.p, sinkA.p);
-    GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, w0.p);
+    GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, wv[0]);
     if (pt.K) GX_LAUNCH(k_pt_gather_d, grid_persistent(8), 256, 0, d.p, pt.ne_rows.p, pt.K, d_k.p);
     if (iters == 0) GX_LAUNCH(k_fill_f64, grid_persistent(4), 256, 0, g->res_f64.p, n, 1.0 / (double)n);
-    double *w_old = w0.p, *w_new = w1.p, *s_in = sinkA.p, *s_out = sinkB.p;
+    int cur = 0;
+    double *s_in = sinkA.p, *s_out = sinkB.p;
+    if (fused) {
+        // nobody may store into a rank's buffers before that rank has initialised them
+        allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
+    }
     for (int it = 0; it < iters; it++) {
         const double *sink_in = s_in;
         unsigned n_sink_in = nparts;
@@ -568,21 +606,29 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         PtArgs a;
         a.col = pt.col.p; a.ne_ptr = pt.ne_ptr.p; a.ne_rows = pt.ne_rows.p; a.tile_k0 = pt.tile_k0.p;
         a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
+        double *w_old = wv[cur], *w_new = wv[cur ^ 1];
+        WOut wout;
+        wout.n = 1;
+        wout.p[0] = w_new;
+        if (fused) {
+            wout.n = c.nranks;
+            for (int r = 0; r < c.nranks; r++) wout.p[r] = (double *)pt.wbuf[cur ^ 1].peer[r];
+        }
         a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
-        a.w_new = w_new;
+        a.w_new = wout;
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
         GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
         if (g_fin)
             GX_LAUNCH(k_pr_tile_fin, g_fin, 256, 0, pt.ne_ptr.p, pt.ne_rows.p, pt.span_k.p, pt.n_span, pt.empty_rows.p, pt.n_empty,
-                      head_part.p, tail_part.p, d.p, pt.pi.p, tele.p, w_new, rank, s_out + g_tiles);
+                      head_part.p, tail_part.p, d.p, pt.pi.p, tele.p, wout, rank, s_out + g_tiles);
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
-        if (it + 1 < iters) allgather_equal(w_new, Dt::F64, pt.seg);
+        if (it + 1 < iters) { if (!fused) allgather_equal(w_new, Dt::F64, pt.seg); }
         else allgatherv(rank, Dt::F64, plan.part);
-        double *t = w_old; w_old = w_new; w_new = t;
-        t = s_in; s_in = s_out; s_out = t;
+        cur ^= 1;
+        double *t = s_in; s_in = s_out; s_out = t;
     }
 }
 

@@ -1,6 +1,8 @@
 // comm.cu -- NCCL collectives on the library stream (see comm.cuh for the sharding model).
 #include <nccl.h>
 
+#include <vector>
+
 #include "comm.cuh"
 
 namespace gx {
@@ -63,6 +65,51 @@ Partition make_even_partition(uint64_t count, uint64_t align)
     p.lo = p.b[c.rank];
     p.hi = p.b[c.rank + 1];
     return p;
+}
+
+void peer_alloc(PeerBuf &b, size_t bytes)
+{
+    Context &c = ctx();
+    b = PeerBuf{};
+    b.bytes = bytes;
+    GX_CUDA(cudaMalloc(&b.local, bytes ? bytes : 16)); // plain cudaMalloc: exportable through cudaIpcGetMemHandle
+    b.peer[c.rank < MAX_PEERS ? c.rank : 0] = b.local;
+    if (c.nranks <= 1 || c.nranks > MAX_PEERS) return;
+    // exchange the 64-byte IPC handles with an all-gather, then map every peer's buffer
+    cudaIpcMemHandle_t mine;
+    GX_CUDA(cudaIpcGetMemHandle(&mine, b.local));
+    DevBuf<cudaIpcMemHandle_t> all(c.nranks);
+    GX_CUDA(cudaMemcpyAsync(all.p + c.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
+    GX_NCCL(ncclAllGather(all.p + c.rank, all.p, sizeof(mine), ncclUint8, (ncclComm_t)c.nccl_comm, c.stream));
+    std::vector<cudaIpcMemHandle_t> h(c.nranks);
+    GX_CUDA(cudaMemcpyAsync(h.data(), all.p, c.nranks * sizeof(mine), cudaMemcpyDeviceToHost, c.stream));
+    GX_CUDA(cudaStreamSynchronize(c.stream));
+    bool ok = true;
+    for (int r = 0; r < c.nranks && ok; r++) {
+        if (r == c.rank) continue;
+        if (cudaIpcOpenMemHandle(&b.peer[r], h[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            b.peer[r] = nullptr;
+            ok = false;
+        }
+    }
+    // all ranks must agree on using the peer path
+    DevBuf<int> flag(1);
+    int hflag = ok ? 1 : 0;
+    GX_CUDA(cudaMemcpyAsync(flag.p, &hflag, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    GX_NCCL(ncclAllReduce(flag.p, flag.p, 1, ncclInt32, ncclMin, (ncclComm_t)c.nccl_comm, c.stream));
+    read_back(&hflag, flag.p, sizeof(int));
+    b.shared = hflag == 1;
+}
+
+void peer_free(PeerBuf &b)
+{
+    Context &c = ctx();
+    if (c.ready) cudaStreamSynchronize(c.stream);
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (b.peer[r] && b.peer[r] != b.local) cudaIpcCloseMemHandle(b.peer[r]);
+    if (b.local) cudaFree(b.local);
+    b = PeerBuf{};
 }
 
 static ncclDataType_t nccl_dt(Dt dt)

@@ -23,6 +23,19 @@ Partition make_partition(const uint64_t *rp0, const uint64_t *rp1, uint64_t n);
 // Even split of [0, count) (work lists that are already balanced per item).
 Partition make_even_partition(uint64_t count, uint64_t align = 1);
 
+// A buffer every rank allocates with the same size and maps into all other ranks (CUDA IPC over
+// NVLink peer access): kernels store their results straight into the peers' copies, so a
+// compute step and the exchange of its output are one kernel ("fused collective").
+constexpr int MAX_PEERS = 8;
+struct PeerBuf {
+    void *local = nullptr;
+    void *peer[MAX_PEERS] = {nullptr}; // peer[r] = rank r's buffer as seen from here (peer[rank] == local)
+    size_t bytes = 0;
+    bool shared = false;               // false: single rank or peer mapping unavailable
+};
+void peer_alloc(PeerBuf &b, size_t bytes);
+void peer_free(PeerBuf &b);
+
 enum class Red { Sum, Min, Max };
 enum class Dt { U32, I32, U64, F64, U8 };
 

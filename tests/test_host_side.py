@@ -85,6 +85,22 @@ def test_relabel_and_readers_roundtrip(tmp_path, name, weighted):
     assert os.path.getsize(tmp_path / "graph.grb") == 512 + 68 + 8 * (g.n + 1) + 8 * g.nnz + (8 * g.nnz if weighted else 1)
 
 
+@pytest.mark.parametrize("name", ["example-directed", "example-undirected", "test-sssp-directed"])
+def test_relabel_drop_in_matches_reference_format(tmp_path, name):
+    """bin/py/relabel.py (DuckDB-free, same flags as the reference's) writes the files load-graph.sh expects."""
+    g, params = load_fixture(name)
+    import sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "bin", "py", "relabel.py"), "--graph-name", name,
+                           "--input-vertex-path", os.path.join(GOLDEN, name + ".v"),
+                           "--input-edge-path", os.path.join(GOLDEN, name + ".e"), "--output-path", str(tmp_path),
+                           "--weighted", str(params["weighted"]).lower(), "--directed", str(params["directed"]).lower()],
+                          stdout=subprocess.DEVNULL)
+    h = graphio.read_vtx_mtx(str(tmp_path))
+    assert np.array_equal(h.rowptr, g.rowptr) and np.array_equal(h.colidx, g.colidx) and np.array_equal(h.mapping, g.mapping)
+    if params["weighted"]:
+        assert np.array_equal(h.weights, g.weights)
+
+
 def test_numpy_grb_writer_matches_cpp_reader_layout(tmp_path):
     g = rmat.rmat_graph(8, directed=True, weighted=True)
     graphio.write_graph_dir(str(tmp_path), g, binary=True)
