@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgxb200.so")
+LIB_PATH = os.environ.get("GX_LIB", os.path.join(_HERE, "lib", "libgxb200.so"))  # GX_LIB: A/B runs of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gxb200.h")
 
 GX_OK = 0

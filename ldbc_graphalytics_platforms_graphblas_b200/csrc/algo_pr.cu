@@ -29,7 +29,7 @@
 //                  partials, hot stage, warp-per-tile gather + segmented sums + fused epilogue
 //                  r -> w' = r/d and sink mass
 //   k_pr_tile_fin  thread per tile-crossing row (ordered sum of its partials) / per empty row
-//   (several GPUs: k_pr_tele + all-reduce of the sink mass, all-gather of w', k_pt_scatter)
+//   (several GPUs: k_pr_tele + all-reduce of the sink mass; w' goes to all ranks by peer stores)
 // Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
 #include <cub/device/device_scan.cuh>
 
@@ -101,15 +101,16 @@ struct PrScalars { double teleport, damping, n; };
 // it completes on a rank after every rank finished these kernels, i.e. after all their peer
 // stores, and a rank reuses a buffer only two iterations later.
 struct WOut {
-    double *p[MAX_PEERS];
-    int n;
+    double *peer[MAX_PEERS - 1];  // the other ranks' copies
+    int npeer;                    // 0 on one GPU
 };
 
-__device__ __forceinline__ void w_store(const WOut &o, uint32_t slot, double v)
+template <bool PEERS>
+__device__ __forceinline__ void w_store(double *__restrict__ own, const WOut *__restrict__ o, uint32_t slot, double v)
 {
-#pragma unroll
-    for (int r = 0; r < MAX_PEERS; r++)
-        if (r < o.n) o.p[r][slot] = v;
+    own[slot] = v;
+    if (PEERS)
+        for (int r = 0; r < o->npeer; r++) o->peer[r][slot] = v;
 }
 
 __global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
@@ -138,6 +139,8 @@ struct PrTiles {
     DevBuf<uint32_t> mask;      // M bits (32 bytes per tile): entry starts a row (tile-first entries excluded)
     DevBuf<uint32_t> slot_k;    // K: pi(vertex of row k), where its w' goes
     DevBuf<uint32_t> span_k;    // n_span: non-empty rows lying in more than one tile
+    // operands of k_pr_tile_fin, one entry per thread so that its loads are independent:
+    DevBuf<uint32_t> fin_v, fin_slot, fin_t0, fin_nt; // n_span + n_empty: vertex, slot of w', first tile, following tiles
     DevBuf<uint32_t> empty_rows; // n_empty
 };
 
@@ -212,18 +215,6 @@ __global__ void k_pt_scatter(const double *__restrict__ w_nat, const uint32_t *_
     for (; v < n; v += stride) w_perm[pi[v]] = w_nat[v];
 }
 
-__device__ __forceinline__ void pt_epilogue(uint32_t v, double s, double tele, const double *__restrict__ d,
-                                            const uint32_t *__restrict__ pi, const WOut &w_new,
-                                            double *__restrict__ rank, double &sink)
-{
-    const double r = tele + s;
-    const double dv = d[v];
-    const uint32_t slot = pi ? pi[v] : v; // one GPU: straight into the degree-sorted space
-    if (dv == 0.0) sink += r;
-    w_store(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
-    if (rank) rank[v] = r;
-}
-
 __global__ void k_pt_tile_k0(const uint64_t *__restrict__ ne_ptr, uint64_t K, uint64_t n_tiles, uint32_t *__restrict__ tile_k0)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,15 +259,17 @@ __global__ void k_pt_gather_d(const double *__restrict__ d, const uint32_t *__re
 }
 
 // epilogue of non-empty row k: r = teleport' + s, w' = r / d, sink mass
+template <bool PEERS>
 __device__ __forceinline__ void pt_close(uint32_t k, double s, double tele, const double *__restrict__ d_k,
                                          const uint32_t *__restrict__ slot_k, const uint32_t *__restrict__ ne_rows,
-                                         const WOut &w_new, double *__restrict__ rank, double &sink)
+                                         double *__restrict__ w_new, const WOut *__restrict__ peers,
+                                         double *__restrict__ rank, double &sink)
 {
     const double r = tele + s;
     const double dv = d_k[k];
     const uint32_t slot = slot_k[k];
     if (dv == 0.0) sink += r;
-    w_store(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
+    w_store<PEERS>(w_new, peers, slot, dv == 0.0 ? 0.0 : r / dv);
     if (rank) rank[ne_rows[k]] = r;
 }
 
@@ -305,7 +298,8 @@ struct PtArgs {
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
     double *tele_out;
-    WOut w_new;
+    double *w_new;          // this rank's copy of the new w
+    const WOut *peers;      // device copy of the other ranks' buffers (several GPUs, fused exchange)
     double *rank;
     double *head_part;
     double *tail_part;
@@ -315,6 +309,7 @@ struct PtArgs {
     PrScalars sc;
 };
 
+template <bool PEERS>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
     extern __shared__ double s_hot[];
@@ -383,7 +378,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
                 for (int j = 0; j < 8; j++)
                     if ((uint32_t)j >= i0 && (uint32_t)j < i) s += val[j];
                 if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
-                else pt_close(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                else pt_close<PEERS>(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
                 kcur++;
                 i0 = i;
             }
@@ -407,14 +402,14 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
             // the row running into this lane ends at the lane's first row start
             const double tot = carry + head;
             if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
-            else pt_close(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+            else pt_close<PEERS>(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
         }
         if (lane == 31) {
             // the row still open at the end of the tile
             const uint32_t klast = k0 + total_starts;
             const bool began_here = total_starts > 0 || k0_starts_here;
             if (ends_here) {
-                if (began_here) pt_close(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                if (began_here) pt_close<PEERS>(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
                 else a.head_part[t] = sv;
             } else {
                 if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
@@ -432,27 +427,55 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
     }
 }
 
+// per-thread operands of k_pr_tile_fin: tile-crossing rows first, then rows without entries
+__global__ void k_pt_fin_plan(const uint64_t *__restrict__ ne_ptr, const uint32_t *__restrict__ ne_rows,
+                              const uint32_t *__restrict__ span_k, uint64_t n_span, const uint32_t *__restrict__ empty_rows,
+                              uint64_t n_empty, const uint32_t *__restrict__ pi, uint32_t *__restrict__ fin_v,
+                              uint32_t *__restrict__ fin_slot, uint32_t *__restrict__ fin_t0, uint32_t *__restrict__ fin_nt)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_span + n_empty; i += stride) {
+        uint32_t v, t0 = 0, nt = 0;
+        if (i < n_span) {
+            const uint32_t k = span_k[i];
+            v = ne_rows[k];
+            t0 = (uint32_t)(ne_ptr[k] / PT_TILE);
+            nt = (uint32_t)((ne_ptr[k + 1] - 1) / PT_TILE) - t0;
+        } else {
+            v = empty_rows[i - n_span];
+        }
+        fin_v[i] = v; fin_slot[i] = pi[v]; fin_t0[i] = t0; fin_nt[i] = nt;
+    }
+}
+
 // rows crossing tile borders (tail of the first tile + heads of the next ones, added in tile
-// order) and rows without entries; one thread each -- the loads of a row are independent
+// order) and rows without entries; one thread each, all operands indexed by the thread
+template <bool PEERS>
 __global__ void __launch_bounds__(256)
-k_pr_tile_fin(const uint64_t *__restrict__ ne_ptr, const uint32_t *__restrict__ ne_rows, const uint32_t *__restrict__ span_k,
-              uint64_t n_span, const uint32_t *__restrict__ empty_rows, uint64_t n_empty, const double *__restrict__ head_part,
-              const double *__restrict__ tail_part, const double *__restrict__ d, const uint32_t *__restrict__ pi,
-              const double *__restrict__ tele_p, const WOut w_new, double *__restrict__ rank,
-              double *__restrict__ sink_part)
+k_pr_tile_fin(const uint32_t *__restrict__ fin_v, const uint32_t *__restrict__ fin_slot, const uint32_t *__restrict__ fin_t0,
+              const uint32_t *__restrict__ fin_nt, const double *__restrict__ fin_d, uint64_t n_span, uint64_t n_fin,
+              const double *__restrict__ head_part, const double *__restrict__ tail_part,
+              const double *__restrict__ tele_p, double *__restrict__ w_new, const WOut *__restrict__ peers,
+              double *__restrict__ rank, double *__restrict__ sink_part)
 {
     const double tele = *tele_p;
     double sink = 0.0;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one row per thread
-    if (i < n_span) {
-        const uint32_t k = span_k[i];
-        const uint64_t t0 = ne_ptr[k] / PT_TILE, t1 = (ne_ptr[k + 1] - 1) / PT_TILE;
-        double s = tail_part[t0];
+    if (i < n_fin) {
+        const double dv = fin_d[i];
+        const uint32_t slot = fin_slot[i];
+        double s = 0.0;
+        if (i < n_span) {
+            const uint32_t t0 = fin_t0[i], nt = fin_nt[i];
+            s = tail_part[t0];
 #pragma unroll 4
-        for (uint64_t t = t0 + 1; t <= t1; t++) s += head_part[t];
-        pt_epilogue(ne_rows[k], s, tele, d, pi, w_new, rank, sink);
-    } else if (i - n_span < n_empty) {
-        pt_epilogue(empty_rows[i - n_span], 0.0, tele, d, pi, w_new, rank, sink);
+            for (uint32_t t = 1; t <= nt; t++) s += head_part[t0 + t];
+        }
+        const double r = tele + s;
+        if (dv == 0.0) sink += r;
+        w_store<PEERS>(w_new, peers, slot, dv == 0.0 ? 0.0 : r / dv);
+        if (rank) rank[fin_v[i]] = r;
     }
     __shared__ double red[8];
     sink = warp_sum(sink);
@@ -460,7 +483,7 @@ k_pr_tile_fin(const uint64_t *__restrict__ ne_ptr, const uint32_t *__restrict__ 
     __syncthreads();
     if (threadIdx.x == 0) {
         double x = 0.0;
-        for (unsigned i = 0; i < (blockDim.x >> 5); i++) x += red[i];
+        for (unsigned i2 = 0; i2 < (blockDim.x >> 5); i2++) x += red[i2];
         sink_part[blockIdx.x] = x;
     }
 }
@@ -540,6 +563,12 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         cnt.zero();
         GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->span_k.p, cnt.p, (uint64_t)ns);
     }
+    const uint64_t n_fin = pt->n_span + pt->n_empty;
+    pt->fin_v.alloc(n_fin ? n_fin : 1); pt->fin_slot.alloc(n_fin ? n_fin : 1);
+    pt->fin_t0.alloc(n_fin ? n_fin : 1); pt->fin_nt.alloc(n_fin ? n_fin : 1);
+    if (n_fin)
+        GX_LAUNCH(k_pt_fin_plan, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->ne_rows.p, pt->span_k.p, pt->n_span,
+                  pt->empty_rows.p, pt->n_empty, pt->pi.p, pt->fin_v.p, pt->fin_slot.p, pt->fin_t0.p, pt->fin_nt.p);
     return pt;
 }
 
@@ -555,7 +584,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
     const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
     const size_t smem = (size_t)hot * sizeof(double);
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PrTiles &ptm = *(PrTiles *)g->pr_cache;
     if (!ptm.have_wbuf) {
         peer_alloc(ptm.wbuf[0], pt.slots * sizeof(double));
@@ -565,7 +595,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     // fused exchange (peer stores from the kernels) unless the mapping failed or GX_PR_FUSED=0
     const char *fe = getenv("GX_PR_FUSED");
     const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && !(fe && fe[0] == '0');
-    DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1);
+    const uint64_t n_fin = pt.n_span + pt.n_empty;
+    DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1), d_fin(n_fin ? n_fin : 1);
     double *wv[2] = {(double *)pt.wbuf[0].local, (double *)pt.wbuf[1].local};
     if (multi()) { // padding slots are exchanged but never gathered
         GX_CUDA(cudaMemsetAsync(wv[0], 0, pt.slots * sizeof(double), c.stream));
@@ -584,9 +615,22 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     GX_LAUNCH(k_pr_init, g_init, 256, 0, g->out.rowptr.p, n, v0, v1, damping, d.p, w_nat.p, sinkA.p);
     GX_LAUNCH(k_pt_scatter, grid_persistent(8), 256, 0, w_nat.p, pt.pi.p, n, wv[0]);
     if (pt.K) GX_LAUNCH(k_pt_gather_d, grid_persistent(8), 256, 0, d.p, pt.ne_rows.p, pt.K, d_k.p);
+    if (n_fin) GX_LAUNCH(k_pt_gather_d, grid_persistent(8), 256, 0, d.p, pt.fin_v.p, n_fin, d_fin.p);
     if (iters == 0) GX_LAUNCH(k_fill_f64, grid_persistent(4), 256, 0, g->res_f64.p, n, 1.0 / (double)n);
     int cur = 0;
     double *s_in = sinkA.p, *s_out = sinkB.p;
+    // peer pointer tables of the two buffers, read by the kernels from global memory
+    DevBuf<WOut> peer_tab(2);
+    {
+        WOut h[2];
+        for (int b = 0; b < 2; b++) {
+            h[b].npeer = 0;
+            for (int r = 0; fused && r < c.nranks; r++)
+                if (r != c.rank) h[b].peer[h[b].npeer++] = (double *)pt.wbuf[b].peer[r];
+        }
+        GX_CUDA(cudaMemcpyAsync(peer_tab.p, h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
+        GX_CUDA(cudaStreamSynchronize(c.stream));
+    }
     if (fused) {
         // nobody may store into a rank's buffers before that rank has initialised them
         allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
@@ -607,22 +651,21 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.col = pt.col.p; a.ne_ptr = pt.ne_ptr.p; a.ne_rows = pt.ne_rows.p; a.tile_k0 = pt.tile_k0.p;
         a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
         double *w_old = wv[cur], *w_new = wv[cur ^ 1];
-        WOut wout;
-        wout.n = 1;
-        wout.p[0] = w_new;
-        if (fused) {
-            wout.n = c.nranks;
-            for (int r = 0; r < c.nranks; r++) wout.p[r] = (double *)pt.wbuf[cur ^ 1].peer[r];
-        }
+        const WOut *wout = peer_tab.p + (cur ^ 1);
         a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
-        a.w_new = wout;
+        a.w_new = w_new;
+        a.peers = wout;
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
-        GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
-        if (g_fin)
-            GX_LAUNCH(k_pr_tile_fin, g_fin, 256, 0, pt.ne_ptr.p, pt.ne_rows.p, pt.span_k.p, pt.n_span, pt.empty_rows.p, pt.n_empty,
-                      head_part.p, tail_part.p, d.p, pt.pi.p, tele.p, wout, rank, s_out + g_tiles);
+        if (fused) GX_LAUNCH(k_pr_tiles<true>, g_tiles, PT_WARPS * 32, smem, a);
+        else GX_LAUNCH(k_pr_tiles<false>, g_tiles, PT_WARPS * 32, smem, a);
+        if (g_fin && fused)
+            GX_LAUNCH(k_pr_tile_fin<true>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
+                      n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
+        else if (g_fin)
+            GX_LAUNCH(k_pr_tile_fin<false>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
+                      n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
         if (it + 1 < iters) { if (!fused) allgather_equal(w_new, Dt::F64, pt.seg); }

@@ -72,9 +72,15 @@ void peer_alloc(PeerBuf &b, size_t bytes)
     Context &c = ctx();
     b = PeerBuf{};
     b.bytes = bytes;
+    if (c.nranks <= 1 || c.nranks > MAX_PEERS) {
+        // nothing to share: take it from the stream-ordered pool like every other buffer
+        GX_CUDA(cudaMallocAsync(&b.local, bytes ? bytes : 16, c.stream));
+        b.pooled = true;
+        b.peer[0] = b.local;
+        return;
+    }
     GX_CUDA(cudaMalloc(&b.local, bytes ? bytes : 16)); // plain cudaMalloc: exportable through cudaIpcGetMemHandle
-    b.peer[c.rank < MAX_PEERS ? c.rank : 0] = b.local;
-    if (c.nranks <= 1 || c.nranks > MAX_PEERS) return;
+    b.peer[c.rank] = b.local;
     // exchange the 64-byte IPC handles with an all-gather, then map every peer's buffer
     cudaIpcMemHandle_t mine;
     GX_CUDA(cudaIpcGetMemHandle(&mine, b.local));
@@ -108,7 +114,7 @@ void peer_free(PeerBuf &b)
     if (c.ready) cudaStreamSynchronize(c.stream);
     for (int r = 0; r < MAX_PEERS; r++)
         if (b.peer[r] && b.peer[r] != b.local) cudaIpcCloseMemHandle(b.peer[r]);
-    if (b.local) cudaFree(b.local);
+    if (b.local) { if (b.pooled) cudaFreeAsync(b.local, c.stream); else cudaFree(b.local); }
     b = PeerBuf{};
 }
 

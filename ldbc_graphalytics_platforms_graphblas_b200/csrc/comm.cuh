@@ -32,6 +32,7 @@ struct PeerBuf {
     void *peer[MAX_PEERS] = {nullptr}; // peer[r] = rank r's buffer as seen from here (peer[rank] == local)
     size_t bytes = 0;
     bool shared = false;               // false: single rank or peer mapping unavailable
+    bool pooled = false;               // allocated from the stream-ordered pool (not exportable)
 };
 void peer_alloc(PeerBuf &b, size_t bytes);
 void peer_free(PeerBuf &b);
