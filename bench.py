@@ -43,6 +43,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(scale, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per PageRank iteration from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(f"rmat{scale}_directed_n{world}")
+        return e and e["pr_iteration_dram_bytes"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -261,9 +273,10 @@ def run_gpu(args):
     def e2e_step():
         h = capi.Graph.from_csr(n, pin_rp.array, pin_ci.array, None, True)   # H2D upload + validation
         t_up = capi.last_timing()
-        h.bfs(src, out=pin_lvl.array)                                           # builds A' on first use, D2H levels
+        # the result is read back where it is written out: on rank 0 (the process that serialises it)
+        h.bfs(src, out=pin_lvl.array if rank == 0 else False)                   # builds A' on first use, D2H levels
         t_b = capi.last_timing()
-        h.pagerank(PR_DAMPING, PR_ITERS, out=pin_rank.array)                    # D2H ranks
+        h.pagerank(PR_DAMPING, PR_ITERS, out=pin_rank.array if rank == 0 else False)  # D2H ranks
         t_p = capi.last_timing()
         h.free()
         e2e_parts.update(upload_h2d_ms=t_up["h2d_ms"], upload_check_ms=t_up["build_ms"], transpose_ms=t_b["build_ms"],
@@ -282,7 +295,9 @@ def run_gpu(args):
     clocks = sampler.stop() if sampler else None
     e2e = {"value": 2 * ev / t_e2e, "unit": "edges+vertices/s", "ms_per_step": 1e3 * t_e2e,
            "h2d_bytes_per_step": int(8 * (n + 1) + 4 * m), "d2h_bytes_per_step": int(16 * n),
-           "entry": "gx_graph_create_csr32 + gx_bfs + gx_pagerank + gx_graph_free, pinned host buffers",
+           "entry": "gx_graph_create_csr32 + gx_bfs + gx_pagerank + gx_graph_free, pinned host buffers"
+                    + ("" if world == 1 else f"; every rank holds the host arrays, uploads 1/{world} of them over PCIe and "
+                       "all-gathers the rest over NVLink; rank 0 reads the results back"),
            "steps": e2e_steps, "breakdown_ms": {k: round(v, 3) for k, v in e2e_parts.items()}}
 
     if rank != 0:
@@ -294,11 +309,14 @@ def run_gpu(args):
     total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
     pr_kernels = {k: v for k, v in prof.items() if k.startswith(("k_pr_", "k_pt_"))}
     pr_ms_per_iter = sum(v[1] for v in pr_kernels.values()) / (prof_steps * PR_ITERS)
+    # per GPU: with N ranks each one streams 1/N of the entries (row blocks are balanced by entry count)
+    # and is measured against one GPU's peak
     roof = {"bound": "hbm", "kernel": "PageRank iteration (" + "+".join(sorted(pr_kernels)) + ")",
-            "achieved": pr_iter_bytes / (pr_ms_per_iter * 1e-3) / 1e9 if pr_ms_per_iter else None,
-            "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-            "bytes_per_launch": pr_iter_bytes, "launch_ms": pr_ms_per_iter,
-            "share_of_step": sum(v[1] for v in pr_kernels.values()) / total_prof_ms, "traffic": None,
+            "achieved": pr_iter_bytes / world / (pr_ms_per_iter * 1e-3) / 1e9 if pr_ms_per_iter else None,
+            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "per": "GPU",
+            "bytes_per_launch": pr_iter_bytes // world, "launch_ms": pr_ms_per_iter,
+            "share_of_step": sum(v[1] for v in pr_kernels.values()) / total_prof_ms,
+            "traffic": ncu_traffic(scale, world),
             "top_kernel": top[0], "top_kernel_share": top[1][1] / total_prof_ms}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
 

@@ -6,6 +6,7 @@
 // Construction-time sorting / compaction uses CUB device primitives (CUDA
 // toolkit headers); the per-algorithm hot loops in algo_*.cu are hand-written.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
 #include <vector>
@@ -70,22 +71,22 @@ __global__ void k_check_sorted(const uint64_t *__restrict__ rowptr, const uint32
     }
 }
 
-// row id of every entry: binary search of the entry offset in rowptr (balanced
-// under degree skew, no per-row loops).
-__global__ void k_expand_rows(const uint64_t *__restrict__ rowptr, uint64_t n, uint64_t m,
-                              uint32_t *__restrict__ row_of_edge)
+// row id of every entry: every non-empty row writes its id at its first entry, an inclusive
+// max-scan spreads it over the row (12 bytes of traffic per entry, no per-entry search and no
+// per-row loop, so degree skew does not matter).
+__global__ void k_row_heads(const uint64_t *__restrict__ rowptr, uint64_t n, uint32_t *__restrict__ row_of_edge)
 {
-    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; e < m; e += stride) {
-        uint64_t lo = 0, hi = n; // find largest r with rowptr[r] <= e
-        while (hi - lo > 1) {
-            uint64_t mid = (lo + hi) >> 1;
-            if (rowptr[mid] <= e) lo = mid; else hi = mid;
-        }
-        row_of_edge[e] = (uint32_t)lo;
+    for (; v < n; v += stride) {
+        const uint64_t a = rowptr[v];
+        if (rowptr[v + 1] > a) row_of_edge[a] = (uint32_t)v;
     }
 }
+
+struct MaxU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
 
 template <class K, int SHIFT>
 __global__ void k_rowptr_from_sorted(const K *__restrict__ keys, uint64_t m, uint64_t n, uint64_t *__restrict__ rowptr)
@@ -105,7 +106,13 @@ __global__ void k_rowptr_from_sorted(const K *__restrict__ keys, uint64_t m, uin
 void expand_row_ids(const uint64_t *rowptr, uint64_t n, uint64_t m, uint32_t *row_of_edge)
 {
     if (!m) return;
-    GX_LAUNCH(k_expand_rows, grid_for(m, 256, 4), 256, 0, rowptr, n, m, row_of_edge);
+    GX_CUDA(cudaMemsetAsync(row_of_edge, 0, m * sizeof(uint32_t), ctx().stream));
+    GX_LAUNCH(k_row_heads, grid_persistent(8), 256, 0, rowptr, n, row_of_edge);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb, row_of_edge, row_of_edge, MaxU32(), (int64_t)m, ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, row_of_edge, row_of_edge, MaxU32(), (int64_t)m, ctx().stream));
+    count_launch();
 }
 
 void rowptr_from_sorted_rows(const uint32_t *sorted_rows, uint64_t m, uint64_t n, uint64_t *rowptr)
@@ -128,6 +135,18 @@ void sort_keys64(DevBuf<uint64_t> &keys, uint64_t count, int end_bit)
     DevBuf<char> tmp(tb);
     GX_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t)count, 0, end_bit, ctx().stream));
     if (db.Current() != keys.p) std::swap(keys.p, alt.p); // sizes are equal; alt frees the other buffer
+}
+
+void sort_keys32(DevBuf<uint32_t> &keys, uint64_t count, int end_bit)
+{
+    if (count < 2) return;
+    DevBuf<uint32_t> alt(keys.n);
+    cub::DoubleBuffer<uint32_t> db(keys.p, alt.p);
+    size_t tb = 0;
+    GX_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t)count, 0, end_bit, ctx().stream));
+    DevBuf<char> tmp(tb);
+    GX_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t)count, 0, end_bit, ctx().stream));
+    if (db.Current() != keys.p) std::swap(keys.p, alt.p);
 }
 
 void sort_pairs64_f64(DevBuf<uint64_t> &keys, DevBuf<double> &vals, uint64_t count, int end_bit)
@@ -197,6 +216,24 @@ void finish_graph(gx_graph *g)
     }
 }
 
+// Host -> device copy of one array.  On several GPUs every rank was handed the same host arrays
+// (the adjacency is replicated, comm.cuh): a rank pushes only its 1/nranks slice over PCIe and the
+// slices are all-gathered over NVLink, so the upload takes 1/nranks of the single-GPU time instead
+// of nranks copies competing for the host's memory and PCIe bandwidth.
+template <class T>
+static void upload_array(T *dst, const T *src, uint64_t count, Dt dt)
+{
+    if (!count) return;
+    if (!multi()) {
+        GX_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+        return;
+    }
+    const Partition part = make_even_partition(count, 64);
+    if (part.hi > part.lo)
+        GX_CUDA(cudaMemcpyAsync(dst + part.lo, src + part.lo, (part.hi - part.lo) * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+    allgatherv(dst, dt, part);
+}
+
 static void upload_common(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t *rowptr, const double *weights,
                           int directed)
 {
@@ -207,12 +244,12 @@ static void upload_common(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t 
     g->directed = directed != 0;
     g->weighted = weights != nullptr;
     g->out.rowptr.alloc(n + 1);
-    if (n) GX_CUDA(cudaMemcpyAsync(g->out.rowptr.p, rowptr, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx().stream));
+    if (n) upload_array(g->out.rowptr.p, rowptr, n + 1, Dt::U64);
     else g->out.rowptr.zero();
     g->out.col.alloc(nnz);
     if (weights) {
         g->out.w.alloc(nnz);
-        if (nnz) GX_CUDA(cudaMemcpyAsync(g->out.w.p, weights, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+        upload_array(g->out.w.p, weights, nnz, Dt::F64);
     }
 }
 
@@ -441,14 +478,20 @@ extern "C" int gx_graph_create_csr(gx_graph **out, uint64_t n, uint64_t nnz, con
                 PhaseTimer t(&ctx().timing.h2d_ms);
                 upload_common(g, n, nnz, rowptr, weights, directed);
                 // GrB_Index (uint64) column ids: staged in chunks and narrowed to 4 bytes on the device
+                // (several GPUs: a rank stages and narrows its slice only, the 4-byte ids are all-gathered)
                 const uint64_t CH = 1ull << 26;
+                const Partition part = make_even_partition(nnz, 64);
                 DevBuf<uint64_t> stage(nnz < CH ? nnz : CH);
                 DevBuf<int> bad(1);
                 bad.zero();
-                for (uint64_t o = 0; o < nnz; o += CH) {
-                    uint64_t c = nnz - o < CH ? nnz - o : CH;
+                for (uint64_t o = part.lo; o < part.hi; o += CH) {
+                    uint64_t c = part.hi - o < CH ? part.hi - o : CH;
                     GX_CUDA(cudaMemcpyAsync(stage.p, colidx + o, c * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx().stream));
                     GX_LAUNCH(k_narrow_u64, grid_persistent(8), 256, 0, stage.p, g->out.col.p + o, c, n, bad.p);
+                }
+                if (multi() && nnz) {
+                    allgatherv(g->out.col.p, Dt::U32, part);
+                    allreduce(bad.p, 1, Dt::I32, Red::Max);
                 }
                 if (nnz && read_flag(bad.p)) throw Error(GX_ERR_INVALID, "column id >= n");
             }
@@ -477,7 +520,7 @@ extern "C" int gx_graph_create_csr32(gx_graph **out, uint64_t n, uint64_t nnz, c
             {
                 PhaseTimer t(&ctx().timing.h2d_ms);
                 upload_common(g, n, nnz, rowptr, weights, directed);
-                if (nnz) GX_CUDA(cudaMemcpyAsync(g->out.col.p, colidx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx().stream));
+                upload_array(g->out.col.p, colidx, nnz, Dt::U32);
             }
             {
                 PhaseTimer t(&ctx().timing.build_ms);

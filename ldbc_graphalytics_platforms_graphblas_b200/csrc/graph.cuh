@@ -44,6 +44,7 @@ void expand_row_ids(const uint64_t *rowptr, uint64_t n, uint64_t m, uint32_t *ro
 void rowptr_from_sorted_rows(const uint32_t *sorted_rows, uint64_t m, uint64_t n, uint64_t *rowptr);
 void rowptr_from_sorted_keys(const uint64_t *sorted_keys, uint64_t m, uint64_t n, uint64_t *rowptr);
 void sort_keys64(DevBuf<uint64_t> &keys, uint64_t count, int end_bit);
+void sort_keys32(DevBuf<uint32_t> &keys, uint64_t count, int end_bit);
 void sort_pairs64_f64(DevBuf<uint64_t> &keys, DevBuf<double> &vals, uint64_t count, int end_bit);
 int bits_for(uint64_t n);
 uint64_t select_flagged(const uint64_t *in, const uint8_t *flags, uint64_t count, DevBuf<uint64_t> &out);

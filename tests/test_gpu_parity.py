@@ -122,6 +122,85 @@ def test_hub_rows(capi, directed):
     check_all(capi, csr_from_edges(n, src, dst, w, directed), src=0)
 
 
+@pytest.mark.parametrize("directed", [True, False])
+@pytest.mark.parametrize("small_frac", [0.02, 0.2, 0.6])
+def test_wcc_giant_plus_small_components(capi, directed, small_frac):
+    """WCC's sampled start (algo_wcc.cu): a giant component plus many small ones whose smallest ids
+    lie INSIDE other components' id ranges.  small_frac 0.02 / 0.2 exercise the rows-outside-S path
+    (incl. edges whose smaller endpoint is outside the giant tree), 0.6 the plain-FastSV fallback.
+    In the directed case every edge points from the larger to the smaller id or at random, so
+    half of the small components are only reachable through in-edges."""
+    n = 60000
+    rng = np.random.default_rng(int(small_frac * 100) + (7 if directed else 0))
+    perm = rng.permutation(n)
+    n_small = int(n * small_frac)
+    giant, small = perm[n_small:], perm[:n_small]
+    # giant: a random tree plus noise, so it is connected but the sample does not see every edge
+    gs = giant[1:]
+    gd = giant[(rng.random(giant.size - 1) * np.arange(1, giant.size)).astype(np.int64)]
+    ns, nd = rng.choice(giant, 3 * giant.size), rng.choice(giant, 3 * giant.size)
+    # small components: chains of 1..6 vertices
+    cs, cd = [], []
+    i = 0
+    while i < n_small:
+        k = int(rng.integers(1, 7))
+        grp = small[i:i + k]
+        cs.append(grp[:-1]); cd.append(grp[1:])
+        i += k
+    # a late bridge: one small chain is attached to the giant by a single edge stored far down a long row
+    src = np.concatenate([gs, ns] + cs)
+    dst = np.concatenate([gd, nd] + cd)
+    if directed:
+        flip = rng.random(src.size) < 0.5
+        src, dst = np.where(flip, dst, src), np.where(flip, src, dst)
+    hg = csr_from_edges(n, src, dst, None, directed)
+    check_all(capi, hg, what="wcc")
+
+
+@pytest.mark.parametrize("directed", [True, False])
+def test_cdlp_active_rows_match_full_recompute(capi, directed, monkeypatch):
+    """CDLP recomputes only rows with a changed neighbour once few rows change (algo_cdlp.cu);
+    the labels must equal both the oracle's and a run with GX_CDLP_ACTIVE=0, for every iteration
+    count (the switch happens around iteration 4-5 on RMAT)."""
+    hg = rmat.rmat_graph(14, directed=directed)
+    n, rp, ci = hg.n, hg.rowptr, hg.colidx
+    g = capi.Graph.from_host(hg)
+    try:
+        for iters in (1, 3, 5, 6, 8, 12, 30):
+            ref = oracle.cdlp(n, rp, ci, directed, iters)
+            monkeypatch.setenv("GX_CDLP_ACTIVE", "1")
+            a = g.cdlp(iters)
+            monkeypatch.setenv("GX_CDLP_ACTIVE", "0")
+            b = g.cdlp(iters)
+            assert np.array_equal(a, ref), f"active rows, {iters} iterations"
+            assert np.array_equal(b, ref), f"full recompute, {iters} iterations"
+    finally:
+        g.free()
+
+
+def test_cdlp_first_iteration_closed_form_and_repeated_entries(capi, monkeypatch):
+    """Undirected graphs take iteration 1 in closed form (label = smallest neighbour) unless a row
+    repeats an entry; a multigraph (dedupe=False) must fall back to counting.  Both against the
+    oracle and against GX_CDLP_FIRST=0."""
+    rng = np.random.default_rng(21)
+    n, m = 3000, 12000
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    src = np.concatenate([src, src[:3000]])   # 3000 edges listed twice
+    dst = np.concatenate([dst, dst[:3000]])
+    for dedupe in (True, False):
+        hg = csr_from_edges(n, src, dst, None, False, dedupe=dedupe)
+        g = capi.Graph.from_host(hg)
+        try:
+            for iters in (1, 2, 10):
+                ref = oracle.cdlp(hg.n, hg.rowptr, hg.colidx, False, iters)
+                monkeypatch.setenv("GX_CDLP_FIRST", "1")
+                assert np.array_equal(g.cdlp(iters), ref), (dedupe, iters)
+                monkeypatch.setenv("GX_CDLP_FIRST", "0")
+                assert np.array_equal(g.cdlp(iters), ref), (dedupe, iters, "general kernels")
+        finally:
+            g.free()
+
+
 def test_lcc_every_apex_size_class(capi):
     """A clique: oriented out-degrees run from 0 to n-1 (long and short lists meet in every
     intersection), and the answer is known in closed form: LCC is exactly 1 everywhere."""
