@@ -16,12 +16,18 @@
 //                     an improved vertex enters the next frontier once (flag)
 //   k_sssp_relax_big  CTA per piece
 // Work efficiency: plain frontier sweeps relax every edge ~4x on RMAT (a vertex is expanded again
-// each time its distance drops).  On one GPU the frontier is therefore bucketed like
-// delta-stepping's (LAGraph's own algorithm): vertices below the current threshold T are expanded
-// now ("near"), the others only get their state marked ("far") and are collected by one pass
-// over the state array when the near queue runs dry and T advances by delta.  delta only
-// schedules work -- the fix-point, hence every bit of the result, is the same.
+// each time its distance drops).  On one GPU the run is therefore delta-stepping proper (Meyer &
+// Sanders; LAGraph's own algorithm): buckets [T - delta, T) are settled in order.  Inside a bucket
+// only LIGHT entries (w <= delta) are relaxed, again whenever a member's distance drops; once the
+// bucket is stable the HEAVY entries of everything it expanded are relaxed ONCE, with final
+// distances -- a heavy entry cannot reach back into the bucket.  A cached copy of the adjacency
+// keeps every row's light entries in front (stable partition, built once per graph and delta:
+// SsspCache).  Targets beyond T only get their state marked ("far") and are collected by one
+// pass over the state array when T advances.  delta only schedules work -- the fix-point, hence
+// every bit of the result, is the same.  Several GPUs still run plain sweeps.
 // Algorithmic bytes (one-pass bound): 12m + 8(n+1) + 16n.
+#include <cub/device/device_scan.cuh>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -33,7 +39,7 @@ namespace gx {
 constexpr uint32_t SSSP_BIG = 4096;
 constexpr unsigned long long INF_BITS = 0x7FF0000000000000ull;
 
-struct SsspCounters { unsigned long long next_count, big_count, relaxed, far_count, far_min; };
+struct SsspCounters { unsigned long long next_count, big_count, relaxed, far_count, far_min, r_count; };
 
 __global__ void k_sssp_init(unsigned long long *__restrict__ dist, uint64_t n, uint32_t src, uint32_t *__restrict__ queue,
                             uint32_t *__restrict__ inq)
@@ -59,6 +65,49 @@ __device__ __forceinline__ bool sssp_relax_edge(unsigned long long *dist, uint32
     if (nb < thresh) { if (state[v] != 1u) state[v] = 1u; return true; }
     atomicCAS(&state[v], 0u, 2u);
     return false;
+}
+
+// read-only adjacency loads the compiler may batch (ld_stream is `asm volatile`, i.e. strictly ordered)
+__device__ __forceinline__ uint32_t ld_adj(const uint32_t *p)
+{
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_adj_f64(const double *p)
+{
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Relax entries e0, e0 + step, ... (up to 4, below `hi`): the 4 entry loads and then the 4 distance
+// loads are in flight together; only actual improvements go on to the atomic.
+__device__ __forceinline__ unsigned sssp_relax4(const uint32_t *__restrict__ col, const double *__restrict__ w, uint64_t e0,
+                                                uint64_t step, uint64_t hi, double du, unsigned long long *dist,
+                                                uint32_t *state, unsigned long long thresh)
+{
+    uint32_t v[4];
+    double nd[4];
+    unsigned long long dv[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint64_t e = e0 + (uint64_t)j * step;
+        ok[j] = e < hi;
+        v[j] = ok[j] ? ld_adj(col + e) : 0u;
+        nd[j] = ok[j] ? du + ld_adj_f64(w + e) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) dv[j] = ok[j] ? dist[v[j]] : 0ull;
+    unsigned cntd = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (!ok[j]) continue;
+        cntd++;
+        if ((unsigned long long)__double_as_longlong(nd[j]) < dv[j]) sssp_relax_edge(dist, state, v[j], nd[j], thresh);
+    }
+    return cntd;
 }
 
 __device__ __forceinline__ void sssp_append(bool won, uint32_t v, uint32_t *next_q, SsspCounters *cnt)
@@ -169,6 +218,149 @@ k_sssp_compact(const uint32_t *__restrict__ state, uint64_t n, uint32_t *__restr
     }
 }
 
+// ---- delta-stepping on one GPU: light / heavy entries -----------------------------------------
+struct SsspCache {
+    double delta = 0.0;
+    DevBuf<uint32_t> col;     // m: every row's light entries (w <= delta) first, then the heavy ones
+    DevBuf<double> w;         // m
+    DevBuf<uint32_t> nlight;  // n: light entries of the row
+};
+
+// flag[e] = 1 for a light entry; one extra item (0) so that the exclusive scan ends with the total
+__global__ void k_sssp_light_flags(const double *__restrict__ w, uint64_t m, double delta, uint32_t *__restrict__ flag)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e <= m; e += stride) flag[e] = (e < m && ld_stream_f64(w + e) <= delta) ? 1u : 0u;
+}
+
+// stable partition of every row into light | heavy: L = exclusive prefix count of light entries
+__global__ void k_sssp_partition(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ row_of, const uint32_t *__restrict__ col,
+                                 const double *__restrict__ w, const uint32_t *__restrict__ L, uint64_t m, double delta,
+                                 uint32_t *__restrict__ col_p, double *__restrict__ w_p, uint32_t *__restrict__ nlight)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) {
+        const uint32_t r = row_of[e];
+        const uint64_t a = rowptr[r], b = rowptr[r + 1];
+        const uint32_t la = L[a], nl = L[b] - la, lr = L[e] - la;
+        const double we = ld_stream_f64(w + e);
+        const uint64_t dst = we <= delta ? a + lr : a + nl + ((e - a) - lr);
+        col_p[dst] = ld_stream(col + e);
+        w_p[dst] = we;
+        if (e == a) nlight[r] = nl;
+    }
+}
+
+// G lanes per queue vertex; HEAVY selects which part of the row is relaxed.  Ranges above 32 * G
+// entries are re-queued as CHUNK pieces for whole CTAs (k_sssp_relax_pieces).  Light expansion stamps
+// the vertex with the current epoch: the stamped vertices are the bucket's members whose heavy
+// entries are still due.
+template <int G, bool HEAVY>
+__global__ void __launch_bounds__(256)
+k_sssp_expand(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ nlight, const uint32_t *__restrict__ col,
+              const double *__restrict__ w, const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ qn_p,
+              unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, uint32_t *__restrict__ stamp, uint32_t epoch,
+              uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, uint64_t *__restrict__ big_end,
+              SsspCounters *__restrict__ cnt, unsigned long long thresh)
+{
+    const unsigned sub = threadIdx.x & (G - 1);
+    uint64_t gi = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) / G;
+    const uint64_t qn = *qn_p;
+    unsigned long long relaxed = 0;
+    for (; gi < qn; gi += ng) {
+        const uint32_t u = queue[gi];
+        const uint64_t a = rowptr[u], b = rowptr[u + 1], mid = a + nlight[u];
+        const uint64_t lo = HEAVY ? mid : a, hi = HEAVY ? b : mid;
+        if (!HEAVY && sub == 0) stamp[u] = epoch;
+        if (hi - lo > 32u * G) { // more than 32 trips of the group: whole CTAs take it over
+            const uint64_t nch = (hi - lo + CHUNK - 1) / CHUNK;
+            const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << ((lane_id() / G) * G)); // groups diverge here
+            unsigned long long pos = 0;
+            if (sub == 0) pos = atomicAdd(&cnt->big_count, (unsigned long long)nch);
+            pos = __shfl_sync(gmask, pos, (lane_id() / G) * G);
+            for (uint64_t k = sub; k < nch; k += G) { big_row[pos + k] = u; big_begin[pos + k] = lo + k * CHUNK; big_end[pos + k] = hi; }
+            continue;
+        }
+        const double du = __longlong_as_double((long long)dist[u]);
+        for (uint64_t e = lo + sub; e < hi; e += 4 * G) relaxed += sssp_relax4(col, w, e, G, hi, du, dist, state, thresh);
+    }
+    relaxed = warp_sum(relaxed);
+    if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
+}
+
+__global__ void __launch_bounds__(256)
+k_sssp_relax_pieces(const uint32_t *__restrict__ col, const double *__restrict__ w, const uint32_t *__restrict__ big_row,
+                    const uint64_t *__restrict__ big_begin, const uint64_t *__restrict__ big_end,
+                    unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, SsspCounters *__restrict__ cnt,
+                    unsigned long long thresh)
+{
+    const unsigned long long nbig = cnt->big_count;
+    unsigned long long relaxed = 0;
+    for (unsigned long long c = blockIdx.x; c < nbig; c += gridDim.x) {
+        const uint64_t b0 = big_begin[c], end = big_end[c];
+        const uint64_t e_end = (b0 + CHUNK < end) ? b0 + CHUNK : end;
+        const double du = __longlong_as_double((long long)dist[big_row[c]]);
+        for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 4 * 256) relaxed += sssp_relax4(col, w, e, 256, e_end, du, dist, state, thresh);
+    }
+    relaxed = warp_sum(relaxed);
+    if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
+}
+
+// Block-level compaction, 4 consecutive vertices per thread: `take` bit j selects vertex v4 + j.  One
+// global atomic per 1024 vertices that hold any (a per-warp atomic on one counter costs ~0.25 us each
+// once hundreds of thousands of warps queue up behind it).  All 256 threads of the CTA must call.
+__device__ __forceinline__ void block_compact4(unsigned take, uint64_t v4, uint32_t *__restrict__ queue,
+                                               unsigned long long *__restrict__ count)
+{
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned mine = __popc(take);
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned up = __shfl_up_sync(FULL, incl, d);
+        if (lane >= (unsigned)d) incl += up;
+    }
+    if (lane == 31) s_cnt[wib] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const unsigned c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+        s_base = tot ? atomicAdd(count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long pos = s_base + s_cnt[wib] + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if ((take >> j) & 1u) queue[pos++] = (uint32_t)(v4 + j);
+    __syncthreads();
+}
+
+// queue of the vertices with arr[v] == value (arr is 16-byte aligned: a stream-ordered allocation)
+__global__ void __launch_bounds__(256)
+k_sssp_compact_eq(const uint32_t *__restrict__ arr, uint32_t value, uint64_t n, uint32_t *__restrict__ queue,
+                  unsigned long long *__restrict__ count)
+{
+    const uint64_t nround = (n + 1023) & ~1023ull;
+    for (uint64_t base = (uint64_t)blockIdx.x * 1024; base < nround; base += (uint64_t)gridDim.x * 1024) {
+        const uint64_t v4 = base + 4ull * threadIdx.x;
+        unsigned take = 0;
+        if (v4 + 4 <= n) {
+            const uint4 x = *(const uint4 *)(arr + v4);
+            take = (x.x == value ? 1u : 0u) | (x.y == value ? 2u : 0u) | (x.z == value ? 4u : 0u) | (x.w == value ? 8u : 0u);
+        } else {
+            for (int j = 0; j < 4; j++)
+                if (v4 + j < n && arr[v4 + j] == value) take |= 1u << j;
+        }
+        block_compact4(take, v4, queue, count);
+    }
+}
+
 __global__ void k_sssp_weight_sum(const double *__restrict__ w, uint64_t m, double *__restrict__ sum)
 {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,21 +373,25 @@ __global__ void k_sssp_weight_sum(const double *__restrict__ w, uint64_t m, doub
 
 // T advanced: far vertices now below it move to the near queue; the rest is counted and its
 // smallest distance recorded so that empty buckets can be skipped
-__global__ void k_sssp_collect_far(const unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, uint64_t n,
-                                   unsigned long long thresh, uint32_t *__restrict__ queue, SsspCounters *__restrict__ cnt)
+__global__ void __launch_bounds__(256)
+k_sssp_collect_far(const unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, uint64_t n,
+                   unsigned long long thresh, uint32_t *__restrict__ queue, SsspCounters *__restrict__ cnt)
 {
-    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t nround = (n + 31) & ~31ull;
+    const uint64_t nround = (n + 1023) & ~1023ull;
     unsigned long long far = 0, fmin = ~0ull;
-    for (; v < nround; v += stride) {
-        bool take = false;
-        if (v < n && state[v] == 2u) {
-            const unsigned long long d = dist[v];
-            if (d < thresh) { take = true; state[v] = 1u; }
-            else { far++; fmin = d < fmin ? d : fmin; }
+    for (uint64_t base = (uint64_t)blockIdx.x * 1024; base < nround; base += (uint64_t)gridDim.x * 1024) {
+        const uint64_t v4 = base + 4ull * threadIdx.x;
+        unsigned take = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t v = v4 + j;
+            if (v < n && state[v] == 2u) {
+                const unsigned long long d = dist[v];
+                if (d < thresh) { take |= 1u << j; state[v] = 1u; }
+                else { far++; fmin = d < fmin ? d : fmin; }
+            }
         }
-        sssp_append(take, (uint32_t)v, queue, cnt);
+        block_compact4(take, v4, queue, &cnt->next_count);
     }
     far = warp_sum(far);
 #pragma unroll
@@ -231,7 +427,122 @@ __global__ void k_sssp_out(const unsigned long long *__restrict__ dist, uint64_t
 
 } // namespace gx
 
+namespace gx {
+
+static SsspCache *build_sssp_cache(gx_graph *g, double delta)
+{
+    const uint64_t n = g->n, m = g->m;
+    GX_REQUIRE(m < 0xFFFFFFFFull, "SSSP light/heavy partition needs nnz < 2^32");
+    SsspCache *sc = new SsspCache();
+    sc->delta = delta;
+    sc->col.alloc(m ? m : 1);
+    sc->w.alloc(m ? m : 1);
+    sc->nlight.alloc(n);
+    sc->nlight.zero();
+    if (!m) return sc;
+    DevBuf<uint32_t> L(m + 1), rows(m);
+    {
+        // L[e] = light entries before e; L[m] = their total
+        GX_LAUNCH(k_sssp_light_flags, grid_persistent(8), 256, 0, g->out.w.p, m, delta, L.p);
+        size_t tb = 0;
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, L.p, L.p, (int64_t)(m + 1), ctx().stream));
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, L.p, L.p, (int64_t)(m + 1), ctx().stream));
+        count_launch();
+    }
+    expand_row_ids(g->out.rowptr.p, n, m, rows.p);
+    GX_LAUNCH(k_sssp_partition, grid_persistent(8), 256, 0, g->out.rowptr.p, rows.p, g->out.col.p, g->out.w.p, L.p, m, delta,
+              sc->col.p, sc->w.p, sc->nlight.p);
+    return sc;
+}
+
+// one GPU: delta-stepping with light / heavy entries (see the header comment)
+static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, uint64_t &relaxed, uint32_t &rounds)
+{
+    Context &c = ctx();
+    const uint64_t n = g->n, m = g->m;
+    const double delta = sc.delta;
+    DevBuf<unsigned long long> dist(n);
+    DevBuf<uint32_t> state(n), stamp(n), q0(n), q1(n);
+    const uint64_t big_cap = m / CHUNK + m / 256 + 16; // pieces of one launch: ranges longer than 32 * 8 entries
+    DevBuf<uint32_t> big_row(big_cap);
+    DevBuf<uint64_t> big_begin(big_cap), big_end(big_cap);
+    DevBuf<SsspCounters> cnt(1);
+    DevBuf<unsigned long long> qn_dev(1);
+    auto bits = [](double x) { unsigned long long b; memcpy(&b, &x, sizeof(b)); return b; };
+    const uint64_t *rp = g->out.rowptr.p;
+    GX_LAUNCH(k_sssp_init, grid_persistent(8), 256, 0, dist.p, n, (uint32_t)src, q0.p, state.p);
+    stamp.zero();
+    uint32_t *queue = q0.p, *next_q = q1.p;
+    uint64_t qn = 1;
+    uint32_t epoch = 1;
+    double T = delta;
+    bool expanded = false; // some vertex was light-expanded since the last heavy phase
+    for (;;) {
+        // ---- light rounds: the bucket's members relax their light entries until nothing below T moves
+        while (qn) {
+            cnt.zero();
+            GX_CUDA(cudaMemcpyAsync(qn_dev.p, &qn, sizeof(qn), cudaMemcpyHostToDevice, c.stream));
+            GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, state.p);
+            // (grid capped: every warp ends with one atomic on the shared counters)
+            const unsigned g_light = grid_for(qn * 8, 256) < grid_persistent(8) ? grid_for(qn * 8, 256) : grid_persistent(8);
+            GX_LAUNCH((k_sssp_expand<8, false>), g_light, 256, 0, rp, sc.nlight.p, sc.col.p, sc.w.p, queue, qn_dev.p,
+                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T));
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.col.p, sc.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
+                      state.p, cnt.p, bits(T));
+            GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, state.p, 1u, n, next_q, &cnt.p->next_count);
+            SsspCounters h;
+            read_back(&h, cnt.p, sizeof(h)); // also orders the host-side qn against its async copy
+            qn = h.next_count;
+            relaxed += h.relaxed;
+            uint32_t *t = queue; queue = next_q; next_q = t;
+            rounds++;
+            expanded = true;
+        }
+        // ---- the bucket is stable: heavy entries of everything it expanded, once, with final distances
+        if (expanded) {
+            cnt.zero();
+            GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, stamp.p, epoch, n, next_q, &cnt.p->r_count);
+            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, rp, sc.nlight.p, sc.col.p, sc.w.p, next_q, &cnt.p->r_count,
+                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T));
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.col.p, sc.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
+                      state.p, cnt.p, bits(T));
+            // a heavy entry adds more than delta to a distance >= T - delta, so nothing lands below T;
+            // should rounding ever say otherwise, the vertex is in state 1 and the bucket simply goes on
+            GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, state.p, 1u, n, queue, &cnt.p->next_count);
+            SsspCounters h;
+            read_back(&h, cnt.p, sizeof(h));
+            relaxed += h.relaxed;
+            rounds++;
+            epoch++;
+            expanded = false;
+            qn = h.next_count;
+            if (qn) continue;
+        }
+        // ---- advance the threshold and collect what now lies below it
+        T += delta;
+        SsspCounters h;
+        for (;;) {
+            cnt.zero();
+            GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
+            GX_LAUNCH(k_sssp_collect_far, grid_persistent(8), 256, 0, dist.p, state.p, n, bits(T), queue, cnt.p);
+            read_back(&h, cnt.p, sizeof(h));
+            if (h.next_count || !h.far_count) break;
+            double fmin;
+            memcpy(&fmin, &h.far_min, sizeof(fmin));
+            T = fmin + delta; // skip the empty buckets
+        }
+        qn = h.next_count;
+        if (!qn) break;
+    }
+    GX_LAUNCH(k_sssp_out, grid_persistent(8), 256, 0, dist.p, n, g->res_f64.p);
+}
+
+} // namespace gx
+
 using namespace gx;
+
+void gx_sssp_cache_free(void *p) { delete (SsspCache *)p; }
 
 extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
 {
@@ -258,6 +569,23 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
             g->have_mean_weight = true;
         }
         g->res_f64.alloc(n);
+        // bucket width: a few average edge weights per average degree (Davidson et al.'s near-far rule)
+        double delta = 8.0 * (double)g->mean_weight * (double)n / (double)(m ? m : 1);
+        if (const char *e = getenv("GX_SSSP_DELTA")) delta = atof(e); // tuning knob; 0 = plain sweeps
+        const char *lh = getenv("GX_SSSP_LH");                        // GX_SSSP_LH=0: near/far without the light/heavy split
+        const bool light_heavy = !multi() && delta > 0.0 && m > 0 && !(lh && lh[0] == '0');
+        uint64_t relaxed = 0;
+        uint32_t rounds = 0;
+        if (light_heavy) {
+            SsspCache *sc = (SsspCache *)g->sssp_cache;
+            if (!sc || sc->delta != delta) {
+                PhaseTimer tb(&c.timing.build_ms);
+                if (sc) { delete sc; g->sssp_cache = nullptr; }
+                g->sssp_cache = sc = build_sssp_cache(g, delta);
+            }
+            PhaseTimer tk(&c.timing.kernel_ms);
+            sssp_delta_stepping(g, *sc, src, relaxed, rounds);
+        } else {
         DevBuf<unsigned long long> dist(n);
         DevBuf<uint32_t> inq(n), q0(n), q1(n);
         DevBuf<unsigned long long> prev(multi() ? n : 0);
@@ -265,8 +593,6 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
         DevBuf<uint32_t> big_row(big_cap);
         DevBuf<uint64_t> big_begin(big_cap);
         DevBuf<SsspCounters> cnt(1);
-        uint64_t relaxed = 0;
-        uint32_t rounds = 0;
         {
             PhaseTimer tk(&c.timing.kernel_ms);
             GX_LAUNCH(k_sssp_init, grid_persistent(8), 256, 0, dist.p, n, (uint32_t)src, q0.p, inq.p);
@@ -274,10 +600,7 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
             uint64_t qn = 1;
             if (multi()) GX_CUDA(cudaMemcpyAsync(prev.p, dist.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream));
             uint32_t *inq_p = multi() ? nullptr : inq.p;
-            // bucket width: a few average edge weights per average degree (Davidson et al.'s near-far rule);
             // several GPUs run plain sweeps (threshold = +inf)
-            double delta = 8.0 * (double)g->mean_weight * (double)n / (double)(m ? m : 1);
-            if (const char *e = getenv("GX_SSSP_DELTA")) delta = atof(e); // tuning knob
             const bool buckets = !multi() && delta > 0.0;
             double T = buckets ? delta : INFINITY;
             auto bits = [](double x) { unsigned long long b; memcpy(&b, &x, sizeof(b)); return b; };
@@ -286,7 +609,7 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
                     cnt.zero();
                     // each rank relaxes the out-edges of the frontier vertices in its row block, on its replica
                     if (!multi()) GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, inq.p);
-                    GX_LAUNCH(k_sssp_relax, grid_for(qn * 32, 256), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue, qn,
+                    GX_LAUNCH(k_sssp_relax, grid_for(qn * 32, 256) < grid_persistent(16) ? grid_for(qn * 32, 256) : grid_persistent(16), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue, qn,
                               part.lo, part.hi, dist.p, inq_p, next_q, big_row.p, big_begin.p, cnt.p, bits(T));
                     GX_LAUNCH(k_sssp_relax_big, grid_persistent(4), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, big_row.p,
                               big_begin.p, dist.p, inq_p, next_q, cnt.p, bits(T));
@@ -322,6 +645,7 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
                 if (!qn) break;
             }
             GX_LAUNCH(k_sssp_out, grid_persistent(8), 256, 0, dist.p, n, g->res_f64.p);
+        }
         }
         c.timing.iterations = rounds;
         c.timing.edges_inspected = relaxed;

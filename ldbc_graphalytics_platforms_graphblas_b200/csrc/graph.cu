@@ -457,8 +457,10 @@ using namespace gx;
 
 void gx_cdlp_plan_free(void *p);
 void gx_pr_cache_free(void *p);
+void gx_sssp_cache_free(void *p);
 gx_graph::~gx_graph()
 {
+    if (sssp_cache) gx_sssp_cache_free(sssp_cache);
     if (cdlp_plan) gx_cdlp_plan_free(cdlp_plan);
     if (pr_cache) gx_pr_cache_free(pr_cache);
 }

@@ -71,6 +71,7 @@ struct gx_graph {
 
     void *cdlp_plan = nullptr;        // gx::CdlpPlan (algo_cdlp.cu), degree bins + spill tables
     void *pr_cache = nullptr;         // gx::PrTiles (algo_pr.cu), tiling of the in-edge entries
+    void *sssp_cache = nullptr;       // gx::SsspCache (algo_sssp.cu), rows partitioned into light | heavy entries
 
     // results of the last run of each algorithm stay on the device
     gx::DevBuf<int64_t> res_i64;

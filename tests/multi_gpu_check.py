@@ -31,6 +31,17 @@ def main():
         src = g.max_degree_vertex()
         res = {"bfs": g.bfs(src), "pr": g.pagerank(0.85, 10), "wcc": g.wcc(), "cdlp": g.cdlp(10), "lcc": g.lcc(),
                "sssp": g.sssp(src)}
+        # the upload path on several GPUs: every rank pushes 1/world of the host arrays, the rest arrives by
+        # all-gather over NVLink -- the device copy must equal the host arrays on every rank (u32 and u64 ids)
+        rp_h, ci_h, w_h = g.download()
+        for ids in (ci_h, ci_h.astype(np.uint64)):
+            h = capi.Graph.from_csr(g.n, rp_h, ids, w_h, directed)
+            rp2, ci2, w2 = h.download()
+            if not (np.array_equal(rp2, rp_h) and np.array_equal(ci2, ci_h) and np.array_equal(w2, w_h)):
+                failures.append((directed, rank, "upload", str(ids.dtype)))
+            if not np.array_equal(h.bfs(src), res["bfs"]):
+                failures.append((directed, rank, "bfs after upload", str(ids.dtype)))
+            h.free()
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(res, gathered, dst=0)
         if rank == 0:
@@ -53,6 +64,9 @@ def main():
                     if not (ok and same):
                         failures.append((directed, r, alg, bool(ok), bool(same)))
         g.free()
+    all_fail = [None] * world
+    dist.all_gather_object(all_fail, failures)
+    failures = [f for fl in all_fail for f in fl]
     if rank == 0:
         print("MULTI_GPU_CHECK", "FAIL " + str(failures) if failures else f"OK world={world} scale={scale}", flush=True)
     dist.barrier()

@@ -201,6 +201,32 @@ def test_cdlp_first_iteration_closed_form_and_repeated_entries(capi, monkeypatch
             g.free()
 
 
+@pytest.mark.parametrize("delta", ["", "1e-3", "0.05", "0.5", "100", "0"])
+@pytest.mark.parametrize("light_heavy", ["1", "0"])
+def test_sssp_bucket_width_never_changes_a_bit(capi, monkeypatch, delta, light_heavy):
+    """delta-stepping with light/heavy entries (algo_sssp.cu): whatever the bucket width -- a thousand
+    buckets, one bucket, the default, plain sweeps (0) -- and with or without the light/heavy split
+    the distances are Dijkstra's bit for bit.  Hub rows exercise the chunked pieces of both parts."""
+    if delta:
+        monkeypatch.setenv("GX_SSSP_DELTA", delta)
+    else:
+        monkeypatch.delenv("GX_SSSP_DELTA", raising=False)
+    monkeypatch.setenv("GX_SSSP_LH", light_heavy)
+    rng = np.random.default_rng(31)
+    n = 20000
+    hub = np.zeros(12000, dtype=np.int64)
+    leaves = rng.choice(np.arange(1, n), 12000, replace=False)
+    ns, nd = rng.integers(0, n, 80000), rng.integers(0, n, 80000)
+    src = np.concatenate([hub, ns])
+    dst = np.concatenate([leaves, nd])
+    w = rng.random(src.size) + 1e-4
+    w[:50] = 0.0                                     # zero weights and exact ties
+    w[50:100] = 0.25
+    for directed in (True, False):
+        check_all(capi, csr_from_edges(n, src, dst, w, directed), src=0, what="sssp")
+    check_all(capi, rmat.rmat_graph(13, directed=False, weighted=True), what="sssp")
+
+
 def test_lcc_every_apex_size_class(capi):
     """A clique: oriented out-degrees run from 0 to n-1 (long and short lists meet in every
     intersection), and the answer is known in closed form: LCC is exactly 1 everywhere."""
