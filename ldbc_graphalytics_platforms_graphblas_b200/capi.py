@@ -54,6 +54,7 @@ def lib():
             "gx_comm_unique_id": [vp], "gx_comm_init": [i32, i32, vp], "gx_comm_destroy": [],
             "gx_graph_create_csr": [pp, u64, u64, vp, vp, vp, i32],
             "gx_graph_create_csr32": [pp, u64, u64, vp, vp, vp, i32],
+            "gx_graph_create_csr32_cached": [pp, u64, u64, vp, vp, vp, i32, ctypes.c_uint],
             "gx_graph_load": [pp, ctypes.c_char_p, i32, i32, pp, ctypes.POINTER(u64)],
             "gx_graph_free": [vp],
             "gx_graph_info": [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(i32), ctypes.POINTER(i32)],
@@ -180,17 +181,22 @@ class Graph:
 
     # -- construction ------------------------------------------------------------------------
     @classmethod
-    def from_csr(cls, n, rowptr, colidx, weights=None, directed=True, mapping=None):
+    def from_csr(cls, n, rowptr, colidx, weights=None, directed=True, mapping=None, cache=0):
         rp = np.ascontiguousarray(rowptr, dtype=np.uint64)
         ci = np.ascontiguousarray(colidx)
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         nnz = int(rp[n]) if n else 0
         h = ctypes.c_void_p()
-        if ci.dtype == np.uint32:
+        if ci.dtype == np.uint32 and cache:
+            # upload and cached structures in one call (the transposition rides along with the upload)
+            _chk(lib().gx_graph_create_csr32_cached(ctypes.byref(h), n, nnz, _p(rp), _p(ci), _p(w), int(directed), int(cache)))
+        elif ci.dtype == np.uint32:
             _chk(lib().gx_graph_create_csr32(ctypes.byref(h), n, nnz, _p(rp), _p(ci), _p(w), int(directed)))
         else:
             ci = np.ascontiguousarray(ci, dtype=np.uint64)
             _chk(lib().gx_graph_create_csr(ctypes.byref(h), n, nnz, _p(rp), _p(ci), _p(w), int(directed)))
+            if cache:
+                _chk(lib().gx_graph_cache(h, int(cache)))
         return cls(h, mapping)
 
     @classmethod

@@ -31,6 +31,7 @@
 //   k_pr_tile_fin  thread per tile-crossing row (ordered sum of its partials) / per empty row
 //   (several GPUs: k_pr_tele + all-reduce of the sink mass; w' goes to all ranks by peer stores)
 // Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -105,6 +106,20 @@ struct WOut {
     int npeer;                    // 0 on one GPU
 };
 
+// k_pr_tiles takes the destinations by value (kernel parameter space): measured 6 % faster on one GPU than
+// reading the table through a pointer, and no slower on several
+struct WOutV {
+    double *p[MAX_PEERS];
+    int n;
+};
+
+__device__ __forceinline__ void w_store_v(const WOutV &o, uint32_t slot, double v)
+{
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (r < o.n) o.p[r][slot] = v;
+}
+
 template <bool PEERS>
 __device__ __forceinline__ void w_store(double *__restrict__ own, const WOut *__restrict__ o, uint32_t slot, double v)
 {
@@ -170,31 +185,33 @@ __global__ void k_pt_fill(const uint64_t *__restrict__ rowptr, uint64_t v0, uint
 // Sort key of the index space w lives in: owner rank first (each rank's rows then occupy one
 // contiguous segment, so the all-gather needs no re-ordering), inside a segment by descending
 // out-degree (the often-gathered entries share cache lines), ties by vertex id.
+// (the sort is stable and the vertices enter it in id order, so the id need not be part of the key: a
+// 32-bit key, 24 + log2(ranks) significant bits, with the vertex as payload)
 __global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64_t n, const uint64_t *__restrict__ bounds,
-                                 int nranks, uint64_t *__restrict__ keys)
+                                 int nranks, uint32_t *__restrict__ keys, uint32_t *__restrict__ vertex)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; v < n; v += stride) {
-        uint64_t owner = 0;
+        uint32_t owner = 0;
         while ((int)owner + 1 < nranks && v >= bounds[owner + 1]) owner++;
         const uint64_t od = out_rowptr[v + 1] - out_rowptr[v];
-        const uint64_t inv = 0xFFFFFFull - (od > 0xFFFFFFull ? 0xFFFFFFull : od);
-        keys[v] = (owner << 56) | (inv << 32) | v;
+        const uint32_t inv = 0xFFFFFFu - (uint32_t)(od > 0xFFFFFFull ? 0xFFFFFFull : od);
+        keys[v] = (owner << 24) | inv;
+        vertex[v] = (uint32_t)v;
     }
 }
 
 // slot of the i-th vertex in sorted order: rank r's vertices fill the first (b[r+1] - b[r]) slots of the
 // segment [r * seg, (r+1) * seg) -- equal, padded segments, so the exchange is one plain all-gather
-__global__ void k_pt_make_pi(const uint64_t *__restrict__ sorted_keys, uint64_t n, const uint64_t *__restrict__ bounds,
-                             uint64_t seg, uint32_t *__restrict__ pi)
+__global__ void k_pt_make_pi(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ sorted_vertex, uint64_t n,
+                             const uint64_t *__restrict__ bounds, uint64_t seg, uint32_t *__restrict__ pi)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const uint64_t key = sorted_keys[i];
-        const uint64_t owner = key >> 56;
-        pi[(uint32_t)key] = (uint32_t)(owner * seg + (i - bounds[owner]));
+        const uint64_t owner = sorted_keys[i] >> 24;
+        pi[sorted_vertex[i]] = (uint32_t)(owner * seg + (i - bounds[owner]));
     }
 }
 
@@ -259,17 +276,15 @@ __global__ void k_pt_gather_d(const double *__restrict__ d, const uint32_t *__re
 }
 
 // epilogue of non-empty row k: r = teleport' + s, w' = r / d, sink mass
-template <bool PEERS>
 __device__ __forceinline__ void pt_close(uint32_t k, double s, double tele, const double *__restrict__ d_k,
                                          const uint32_t *__restrict__ slot_k, const uint32_t *__restrict__ ne_rows,
-                                         double *__restrict__ w_new, const WOut *__restrict__ peers,
-                                         double *__restrict__ rank, double &sink)
+                                         const WOutV &w_new, double *__restrict__ rank, double &sink)
 {
     const double r = tele + s;
     const double dv = d_k[k];
     const uint32_t slot = slot_k[k];
     if (dv == 0.0) sink += r;
-    w_store<PEERS>(w_new, peers, slot, dv == 0.0 ? 0.0 : r / dv);
+    w_store_v(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
     if (rank) rank[ne_rows[k]] = r;
 }
 
@@ -298,8 +313,7 @@ struct PtArgs {
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
     double *tele_out;
-    double *w_new;          // this rank's copy of the new w
-    const WOut *peers;      // device copy of the other ranks' buffers (several GPUs, fused exchange)
+    WOutV w_new;            // where w' goes: this rank's copy (+ every peer's on several GPUs, fused exchange)
     double *rank;
     double *head_part;
     double *tail_part;
@@ -309,7 +323,6 @@ struct PtArgs {
     PrScalars sc;
 };
 
-template <bool PEERS>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
     extern __shared__ double s_hot[];
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
                 for (int j = 0; j < 8; j++)
                     if ((uint32_t)j >= i0 && (uint32_t)j < i) s += val[j];
                 if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
-                else pt_close<PEERS>(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
+                else pt_close(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
                 kcur++;
                 i0 = i;
             }
@@ -402,14 +415,14 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
             // the row running into this lane ends at the lane's first row start
             const double tot = carry + head;
             if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
-            else pt_close<PEERS>(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
+            else pt_close(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
         }
         if (lane == 31) {
             // the row still open at the end of the tile
             const uint32_t klast = k0 + total_starts;
             const bool began_here = total_starts > 0 || k0_starts_here;
             if (ends_here) {
-                if (began_here) pt_close<PEERS>(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.peers, a.rank, sink);
+                if (began_here) pt_close(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
                 else a.head_part[t] = sv;
             } else {
                 if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
@@ -493,9 +506,11 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     PrTiles *pt = new PrTiles();
     Adj &in = g->in_adj();
     const uint64_t v0 = in.plan.part.lo, v1 = in.plan.part.hi, nv = v1 - v0;
-    uint64_t ends[2] = {0, 0};
-    read_back(&ends[0], in.rowptr.p + v0, sizeof(uint64_t));
-    read_back(&ends[1], in.rowptr.p + v1, sizeof(uint64_t));
+    uint64_t ends[2] = {0, in.col.n}; // the whole adjacency on one GPU
+    if (multi()) {
+        read_back(&ends[0], in.rowptr.p + v0, sizeof(uint64_t));
+        read_back(&ends[1], in.rowptr.p + v1, sizeof(uint64_t));
+    }
     const uint64_t e0 = ends[0];
     pt->M = ends[1] - ends[0];
     pt->n_tiles = (pt->M + PT_TILE - 1) / PT_TILE;
@@ -525,18 +540,27 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     {
         const uint64_t n = g->n;
         pt->pi.alloc(n);
-        DevBuf<uint64_t> keys(n);
+        DevBuf<uint32_t> keys(n), keys_alt(n), vtx(n), vtx_alt(n);
         DevBuf<uint64_t> bounds(in.plan.part.b.size());
         GX_CUDA(cudaMemcpyAsync(bounds.p, in.plan.part.b.data(), in.plan.part.b.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
                                 ctx().stream));
-        GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, bounds.p, ctx().nranks, keys.p);
-        sort_keys64(keys, n, 64);
+        GX_REQUIRE(ctx().nranks <= 256, "too many ranks");
+        GX_LAUNCH(k_pt_degree_keys, grid_persistent(8), 256, 0, g->out.rowptr.p, n, bounds.p, ctx().nranks, keys.p, vtx.p);
+        cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p), dv(vtx.p, vtx_alt.p);
+        {
+            const int end_bit = 24 + (ctx().nranks > 1 ? bits_for((uint64_t)ctx().nranks) : 0);
+            size_t tb = 0;
+            GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t)n, 0, end_bit, ctx().stream));
+            DevBuf<char> tmp(tb);
+            GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t)n, 0, end_bit, ctx().stream));
+            count_launch();
+        }
         uint64_t seg = 0;
         for (int r = 0; r < ctx().nranks; r++) seg = std::max<uint64_t>(seg, in.plan.part.b[r + 1] - in.plan.part.b[r]);
         pt->seg = (seg + 31) & ~31ull;
         pt->slots = pt->seg * (uint64_t)ctx().nranks;
         GX_REQUIRE(pt->slots < 0xFFFFFFFFull, "vertex slot space exceeds 32 bits");
-        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, keys.p, n, bounds.p, pt->seg, pt->pi.p);
+        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->seg, pt->pi.p);
     }
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
     pt->col.alloc(pt->M ? pt->M : 1);
@@ -553,16 +577,12 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     }
     DevBuf<unsigned long long> cnt(1);
     cnt.zero();
-    DevBuf<uint32_t> dummy(1);
-    if (pt->K) GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, dummy.p, cnt.p, (uint64_t)0);
+    pt->span_k.alloc(pt->n_tiles ? pt->n_tiles : 1); // a spanning row crosses a tile border: at most n_tiles of them
+    if (pt->K) GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->span_k.p, cnt.p, pt->n_tiles);
     unsigned long long ns = 0;
     read_back(&ns, cnt.p, sizeof(ns));
     pt->n_span = ns;
-    pt->span_k.alloc(ns ? ns : 1);
-    if (ns) {
-        cnt.zero();
-        GX_LAUNCH(k_pt_collect_span, grid_persistent(8), 256, 0, pt->ne_ptr.p, pt->K, pt->span_k.p, cnt.p, (uint64_t)ns);
-    }
+    sort_keys32(pt->span_k, ns, bits_for(pt->K + 1)); // the atomics appended in any order; a fixed order keeps the sink sums reproducible
     const uint64_t n_fin = pt->n_span + pt->n_empty;
     pt->fin_v.alloc(n_fin ? n_fin : 1); pt->fin_slot.alloc(n_fin ? n_fin : 1);
     pt->fin_t0.alloc(n_fin ? n_fin : 1); pt->fin_nt.alloc(n_fin ? n_fin : 1);
@@ -584,8 +604,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
     const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
     const size_t smem = (size_t)hot * sizeof(double);
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PrTiles &ptm = *(PrTiles *)g->pr_cache;
     if (!ptm.have_wbuf) {
         peer_alloc(ptm.wbuf[0], pt.slots * sizeof(double));
@@ -653,13 +672,16 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         double *w_old = wv[cur], *w_new = wv[cur ^ 1];
         const WOut *wout = peer_tab.p + (cur ^ 1);
         a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
-        a.w_new = w_new;
-        a.peers = wout;
+        a.w_new.n = 1;
+        a.w_new.p[0] = w_new;
+        if (fused) {
+            a.w_new.n = c.nranks;
+            for (int r = 0; r < c.nranks; r++) a.w_new.p[r] = (double *)pt.wbuf[cur ^ 1].peer[r];
+        }
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
-        if (fused) GX_LAUNCH(k_pr_tiles<true>, g_tiles, PT_WARPS * 32, smem, a);
-        else GX_LAUNCH(k_pr_tiles<false>, g_tiles, PT_WARPS * 32, smem, a);
+        GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
         if (g_fin && fused)
             GX_LAUNCH(k_pr_tile_fin<true>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
                       n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);

@@ -21,8 +21,8 @@ inline gx_graph *UploadGraph(const HostMatrix &A, bool directed, unsigned cache)
 {
     ComputationTimer timer{"Uploading the matrix"};
     gx_graph *G = nullptr;
-    OK(gx_graph_create_csr32(&G, A.nrows, A.nvals, A.Ap.data(), A.Aj.data(), A.iso ? nullptr : A.Ax.data(), directed ? 1 : 0));
-    if (cache) OK(gx_graph_cache(G, cache));
+    OK(gx_graph_create_csr32_cached(&G, A.nrows, A.nvals, A.Ap.data(), A.Aj.data(), A.iso ? nullptr : A.Ax.data(), directed ? 1 : 0,
+                                    cache));
     return G;
 }
 

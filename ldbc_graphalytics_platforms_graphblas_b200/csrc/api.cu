@@ -7,7 +7,7 @@
 #include <map>
 #include <vector>
 
-#include "common.cuh"
+#include "comm.cuh"
 
 namespace gx {
 
@@ -147,6 +147,7 @@ extern "C" int gx_finalize(void)
         Context &c = ctx();
         if (!c.ready) return;
         cudaStreamSynchronize(c.stream);
+        peer_cache_clear();
         if (c.nccl_comm) { ncclCommDestroy((ncclComm_t)c.nccl_comm); c.nccl_comm = nullptr; }
         if (c.flush_buf) cudaFree(c.flush_buf);
         cudaFreeHost(c.pinned_scratch);
@@ -290,6 +291,7 @@ extern "C" int gx_comm_destroy(void)
 {
     return guarded([&] {
         Context &c = ctx();
+        peer_cache_clear();
         if (c.nccl_comm) {
             cudaStreamSynchronize(c.stream);
             GX_NCCL(ncclCommDestroy((ncclComm_t)c.nccl_comm));

@@ -67,11 +67,44 @@ Partition make_even_partition(uint64_t count, uint64_t align)
     return p;
 }
 
+// Mapped buffers released by a graph are parked here and handed to the next graph that asks for a
+// similar size: cudaMalloc + cudaIpcOpenMemHandle on every rank and cudaIpcCloseMemHandle + cudaFree
+// cost ~15 ms per graph.  Every rank allocates and frees in the same order with the same sizes, so
+// the ranks' caches stay in lock-step and a reused buffer is mapped on all of them.
+static std::vector<PeerBuf> g_parked;
+constexpr size_t MAX_PARKED = 4;
+
+static void peer_release(PeerBuf &b)
+{
+    Context &c = ctx();
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (b.peer[r] && b.peer[r] != b.local) cudaIpcCloseMemHandle(b.peer[r]);
+    if (b.local) { if (b.pooled) cudaFreeAsync(b.local, c.stream); else cudaFree(b.local); }
+    b = PeerBuf{};
+}
+
+void peer_cache_clear()
+{
+    if (g_parked.empty()) return;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    for (PeerBuf &p : g_parked) peer_release(p);
+    g_parked.clear();
+}
+
 void peer_alloc(PeerBuf &b, size_t bytes)
 {
     Context &c = ctx();
     b = PeerBuf{};
+    for (size_t i = 0; i < g_parked.size(); i++) {
+        if (g_parked[i].capacity >= bytes && g_parked[i].capacity <= 2 * bytes + 4096) {
+            b = g_parked[i];
+            b.bytes = bytes;
+            g_parked.erase(g_parked.begin() + i);
+            return;
+        }
+    }
     b.bytes = bytes;
+    b.capacity = bytes ? bytes : 16;
     if (c.nranks <= 1 || c.nranks > MAX_PEERS) {
         // nothing to share: take it from the stream-ordered pool like every other buffer
         GX_CUDA(cudaMallocAsync(&b.local, bytes ? bytes : 16, c.stream));
@@ -111,11 +144,13 @@ void peer_alloc(PeerBuf &b, size_t bytes)
 void peer_free(PeerBuf &b)
 {
     Context &c = ctx();
+    if (b.shared && c.nccl_comm && g_parked.size() < MAX_PARKED) { // keep the mapping for the next graph
+        g_parked.push_back(b);
+        b = PeerBuf{};
+        return;
+    }
     if (c.ready) cudaStreamSynchronize(c.stream);
-    for (int r = 0; r < MAX_PEERS; r++)
-        if (b.peer[r] && b.peer[r] != b.local) cudaIpcCloseMemHandle(b.peer[r]);
-    if (b.local) { if (b.pooled) cudaFreeAsync(b.local, c.stream); else cudaFree(b.local); }
-    b = PeerBuf{};
+    peer_release(b);
 }
 
 static ncclDataType_t nccl_dt(Dt dt)

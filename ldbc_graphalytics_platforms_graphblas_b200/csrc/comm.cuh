@@ -30,12 +30,13 @@ constexpr int MAX_PEERS = 8;
 struct PeerBuf {
     void *local = nullptr;
     void *peer[MAX_PEERS] = {nullptr}; // peer[r] = rank r's buffer as seen from here (peer[rank] == local)
-    size_t bytes = 0;
+    size_t bytes = 0, capacity = 0;    // requested / allocated
     bool shared = false;               // false: single rank or peer mapping unavailable
     bool pooled = false;               // allocated from the stream-ordered pool (not exportable)
 };
 void peer_alloc(PeerBuf &b, size_t bytes);
 void peer_free(PeerBuf &b);
+void peer_cache_clear(); // releases the buffers parked for reuse (before the communicator goes away)
 
 enum class Red { Sum, Min, Max };
 enum class Dt { U32, I32, U64, F64, U8 };

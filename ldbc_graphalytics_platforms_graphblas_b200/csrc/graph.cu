@@ -9,6 +9,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "graph.cuh"
@@ -280,6 +282,215 @@ void ensure_in_adj(gx_graph *g)
     g->have_in = true;
 }
 
+// ------------------------------------------------------------------------- pipelined upload + transposition
+// gx_graph_create_csr32_cached(..., GX_CACHE_AT) on one GPU: the column ids go up in row-block chunks
+// on a copy stream; while chunk k+1 is on the PCIe bus, chunk k is validated, its entries get their row
+// ids, a column histogram and a chunk-local stable radix sort by column ("run" k).  Rows ascend
+// from run to run, so the in-edge adjacency is, per column, run 0's segment followed by run 1's, ...
+// -- after the last chunk only its sort, one prefix pass over the histograms and ONE merge pass
+// (8 B read, 4 B written per entry) remain, instead of a full 3-pass sort of all pairs after the
+// upload has finished.
+constexpr int UP_MAX_CHUNKS = 8;
+struct ChunkBounds { uint64_t e[UP_MAX_CHUNKS + 1]; int k; };
+
+__global__ void k_check_rowptr(const uint64_t *__restrict__ rowptr, uint64_t n, uint64_t m, int *__restrict__ bad)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) {
+        const uint64_t a = rowptr[v], b = rowptr[v + 1];
+        if (a > b || b > m || (v == 0 && a != 0) || (v == n - 1 && b != m)) *bad = 1;
+    }
+}
+
+// column ids of [e_lo, e_hi) in range; a decrease inside the chunk is legal only at a row start
+__global__ void k_check_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t n, uint64_t e_lo,
+                              uint64_t e_hi, int *__restrict__ bad, int *__restrict__ unsorted)
+{
+    uint64_t e = e_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < e_hi; e += stride) {
+        const uint32_t c = col[e];
+        if (c >= n) { *bad = 1; continue; }
+        if (e == e_lo || c >= col[e - 1]) continue;
+        uint64_t lo = 0, hi = n; // is there a row r with rowptr[r] == e ?
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] < e) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= n || rowptr[lo] != e) *unsorted = 1;
+    }
+}
+
+__global__ void k_row_heads_range(const uint64_t *__restrict__ rowptr, uint64_t r_lo, uint64_t r_hi, uint64_t e_lo,
+                                  uint64_t e_hi, uint32_t *__restrict__ row_of_edge)
+{
+    uint64_t v = r_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < r_hi; v += stride) {
+        const uint64_t a = rowptr[v];
+        if (rowptr[v + 1] > a && a >= e_lo && a < e_hi) row_of_edge[a - e_lo] = (uint32_t)v; // (offsets not yet known to be sane)
+    }
+}
+
+// rs[k][c] = first position of column c inside run k (n + 1 offsets per run)
+__global__ void k_sum_runs(const uint64_t *__restrict__ rs, int K, uint64_t n, uint64_t *__restrict__ total)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; c <= n; c += stride) {
+        uint64_t t = 0;
+        if (c < n)
+            for (int k = 0; k < K; k++) t += rs[(uint64_t)k * (n + 1) + c + 1] - rs[(uint64_t)k * (n + 1) + c];
+        total[c] = t;
+    }
+}
+
+// delta[k][c] + (position inside run k) = destination of a run entry with column c
+__global__ void k_run_delta(const uint64_t *__restrict__ in_rowptr, const uint64_t *__restrict__ rs, int K, uint64_t n,
+                            uint64_t *__restrict__ delta)
+{
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; c < n; c += stride) {
+        uint64_t acc = in_rowptr[c];
+        for (int k = 0; k < K; k++) {
+            const uint64_t a = rs[(uint64_t)k * (n + 1) + c], b = rs[(uint64_t)k * (n + 1) + c + 1];
+            delta[(uint64_t)k * n + c] = acc - a;
+            acc += b - a;
+        }
+    }
+}
+
+__global__ void k_merge_runs(const uint32_t *__restrict__ run_keys, const uint32_t *__restrict__ run_vals, const ChunkBounds cb,
+                             const uint64_t *__restrict__ delta, uint64_t n, uint32_t *__restrict__ in_col)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t m = cb.e[cb.k];
+    for (; e < m; e += stride) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < UP_MAX_CHUNKS; j++) k += (j < cb.k && e >= cb.e[j]) ? 1 : 0;
+        const uint32_t c = run_keys[e];
+        if (c < n) in_col[delta[(uint64_t)k * n + c] + (e - cb.e[k])] = run_vals[e]; // c >= n: rejected below
+    }
+}
+
+// returns false (nothing uploaded yet) when the shortcut does not apply; throws on invalid input
+static bool upload_transpose_pipelined(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t *rowptr, const uint32_t *colidx,
+                                       const double *weights)
+{
+    Context &c = ctx();
+    if (multi() || n == 0 || nnz < (1ull << 21) || nnz >= 0xFFFFFFFFull) return false;
+    if (const char *e = getenv("GX_UPLOAD_PIPELINE")) if (e[0] == '0') return false;
+    // row-block chunks of about equal entry counts, read off the caller's (host) offsets
+    ChunkBounds cb;
+    uint64_t rows[UP_MAX_CHUNKS + 1];
+    int K = (int)std::min<uint64_t>(UP_MAX_CHUNKS, nnz >> 20);
+    if (rowptr[0] != 0 || rowptr[n] != nnz) return false; // the plain path reports it
+    rows[0] = 0;
+    cb.e[0] = 0;
+    int kk = 0;
+    for (int k = 1; k < K; k++) {
+        const uint64_t target = (uint64_t)(((unsigned __int128)nnz * (unsigned)k) / (unsigned)K);
+        uint64_t r = (uint64_t)(std::lower_bound(rowptr, rowptr + n + 1, target) - rowptr);
+        if (r > n) r = n;
+        const uint64_t e = rowptr[r];
+        if (e > nnz || e < cb.e[kk] || r < rows[kk]) return false; // offsets not monotone: the plain path reports it
+        if (e == cb.e[kk]) continue;
+        kk++;
+        rows[kk] = r;
+        cb.e[kk] = e;
+    }
+    if (cb.e[kk] < nnz) { kk++; rows[kk] = n; cb.e[kk] = nnz; } else rows[kk] = n;
+    K = kk;
+    cb.k = K;
+    for (int k = K + 1; k <= UP_MAX_CHUNKS; k++) cb.e[k] = nnz;
+    uint64_t max_chunk = 0;
+    for (int k = 0; k < K; k++) max_chunk = std::max(max_chunk, cb.e[k + 1] - cb.e[k]);
+
+    static cudaStream_t copy_stream = nullptr;
+    static cudaEvent_t ev_ready = nullptr, ev_chunk[UP_MAX_CHUNKS + 1], ev_t[3]; // ev_t: start / copies done / all done
+    if (!copy_stream) {
+        GX_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        GX_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+        for (auto &e : ev_t) GX_CUDA(cudaEventCreate(&e));
+        for (auto &e : ev_chunk) GX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t s = c.stream;
+    const int bits = bits_for(n);
+    g->out.rowptr.alloc(n + 1);
+    g->out.col.alloc(nnz);
+    if (weights) g->out.w.alloc(nnz);
+    g->in.rowptr.alloc(n + 1);
+    g->in.col.alloc(nnz);
+    DevBuf<uint32_t> run_keys(nnz), run_vals(nnz), chunk_rows(max_chunk);
+    DevBuf<uint64_t> runstart((uint64_t)K * (n + 1)), delta((uint64_t)K * n), total(n + 1);
+    DevBuf<int> flags(2);
+    size_t tb_sort = 0, tb_scan = 0, tb_scan64 = 0;
+    GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                            (uint32_t *)nullptr, (int64_t)max_chunk, 0, bits, s));
+    GX_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb_scan, (uint32_t *)nullptr, (uint32_t *)nullptr, MaxU32(), (int64_t)max_chunk, s));
+    GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb_scan64, (uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)(n + 1), s));
+    DevBuf<char> tmp(std::max(std::max(tb_sort, tb_scan), tb_scan64));
+    flags.zero();
+    GX_CUDA(cudaEventRecord(ev_t[0], s));
+    GX_CUDA(cudaEventRecord(ev_ready, s)); // the copy stream must not touch the buffers before they exist
+    GX_CUDA(cudaStreamWaitEvent(copy_stream, ev_ready, 0));
+    GX_CUDA(cudaMemcpyAsync(g->out.rowptr.p, rowptr, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy_stream));
+    GX_CUDA(cudaEventRecord(ev_chunk[UP_MAX_CHUNKS], copy_stream));
+    for (int k = 0; k < K; k++) {
+        GX_CUDA(cudaMemcpyAsync(g->out.col.p + cb.e[k], colidx + cb.e[k], (cb.e[k + 1] - cb.e[k]) * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, copy_stream));
+        GX_CUDA(cudaEventRecord(ev_chunk[k], copy_stream));
+    }
+    if (weights) GX_CUDA(cudaMemcpyAsync(g->out.w.p, weights, nnz * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+    GX_CUDA(cudaEventRecord(ev_t[1], copy_stream));
+    GX_CUDA(cudaEventRecord(ev_ready, copy_stream)); // reused: "all copies done"
+    GX_CUDA(cudaStreamWaitEvent(s, ev_chunk[UP_MAX_CHUNKS], 0));
+    GX_LAUNCH(k_check_rowptr, grid_persistent(4), 256, 0, g->out.rowptr.p, n, nnz, flags.p);
+    for (int k = 0; k < K; k++) {
+        const uint64_t e0 = cb.e[k], e1 = cb.e[k + 1], cnt = e1 - e0;
+        GX_CUDA(cudaStreamWaitEvent(s, ev_chunk[k], 0));
+        GX_LAUNCH(k_check_chunk, grid_persistent(4), 256, 0, g->out.rowptr.p, g->out.col.p, n, e0, e1, flags.p, flags.p + 1);
+        GX_CUDA(cudaMemsetAsync(chunk_rows.p, 0, cnt * sizeof(uint32_t), s));
+        GX_LAUNCH(k_row_heads_range, grid_persistent(4), 256, 0, g->out.rowptr.p, rows[k], rows[k + 1], e0, e1, chunk_rows.p);
+        GX_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb_scan, chunk_rows.p, chunk_rows.p, MaxU32(), (int64_t)cnt, s));
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb_sort, (const uint32_t *)(g->out.col.p + e0), run_keys.p + e0,
+                                                (const uint32_t *)chunk_rows.p, run_vals.p + e0, (int64_t)cnt, 0, bits, s));
+        rowptr_from_sorted_rows(run_keys.p + e0, cnt, n, runstart.p + (uint64_t)k * (n + 1)); // binary search per column
+        count_launch(2);
+    }
+    GX_LAUNCH(k_sum_runs, grid_persistent(8), 256, 0, runstart.p, K, n, total.p);
+    GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb_scan64, total.p, g->in.rowptr.p, (int64_t)(n + 1), s));
+    GX_LAUNCH(k_run_delta, grid_persistent(8), 256, 0, g->in.rowptr.p, runstart.p, K, n, delta.p);
+    GX_LAUNCH(k_merge_runs, grid_persistent(8), 256, 0, run_keys.p, run_vals.p, cb, delta.p, n, g->in.col.p);
+    GX_CUDA(cudaStreamWaitEvent(s, ev_ready, 0)); // weights (and everything else on the copy stream)
+    GX_CUDA(cudaEventRecord(ev_t[2], s));
+    int h[2] = {0, 0};
+    read_back(h, flags.p, sizeof(h));
+    {
+        // h2d_ms: until the last byte arrived; build_ms: what validation + transposition add after it
+        float up = 0, all = 0;
+        GX_CUDA(cudaEventElapsedTime(&up, ev_t[0], ev_t[1]));
+        GX_CUDA(cudaEventElapsedTime(&all, ev_t[0], ev_t[2]));
+        c.timing.h2d_ms += up;
+        c.timing.build_ms += all > up ? all - up : 0.0;
+    }
+    if (h[0]) throw Error(GX_ERR_INVALID, "CSR arrays are inconsistent (rowptr not monotone or column id >= n)");
+    g->have_in = true;
+    if (h[1]) {
+        // jumbled rows: sort them the usual way and redo the transposition from the sorted rows
+        g->have_in = false;
+        g->in.rowptr.release();
+        g->in.col.release();
+        finish_graph(g);
+        ensure_in_adj(g);
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------- LCC cache
 // key = (a << 33) | (b << 1) | rev : rev = 0 for (a,b) in A, 1 for the mirrored copy of (b,a)
 __global__ void k_lcc_keys(const uint32_t *__restrict__ row, const uint32_t *__restrict__ col, uint64_t m,
@@ -528,6 +739,48 @@ extern "C" int gx_graph_create_csr32(gx_graph **out, uint64_t n, uint64_t nnz, c
                 PhaseTimer t(&ctx().timing.build_ms);
                 finish_graph(g);
             }
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        *out = g;
+    });
+}
+
+extern "C" int gx_graph_create_csr32_cached(gx_graph **out, uint64_t n, uint64_t nnz, const uint64_t *rowptr,
+                                            const uint32_t *colidx, const double *weights, int directed, unsigned cache)
+{
+    return guarded([&] {
+        require_ready();
+        GX_REQUIRE(out != nullptr, "graph handle is NULL");
+        GX_REQUIRE(colidx != nullptr || nnz == 0, "colidx is NULL");
+        GX_REQUIRE(rowptr != nullptr || n == 0, "rowptr is NULL");
+        GX_REQUIRE(n < 0xFFFFFFFEull, "n must be < 2^32 - 2");
+        ctx().timing = gx_timing{};
+        gx_graph *g = new gx_graph();
+        try {
+            g->n = n;
+            g->m = nnz;
+            g->directed = directed != 0;
+            g->weighted = weights != nullptr;
+            bool done = false;
+            if (g->directed && (cache & GX_CACHE_AT)) // upload with the transposition riding along
+                done = upload_transpose_pipelined(g, n, nnz, rowptr, colidx, weights);
+            if (!done) {
+                {
+                    PhaseTimer t(&ctx().timing.h2d_ms);
+                    upload_common(g, n, nnz, rowptr, weights, directed);
+                    upload_array(g->out.col.p, colidx, nnz, Dt::U32);
+                }
+                PhaseTimer t(&ctx().timing.build_ms);
+                finish_graph(g);
+                if (cache & GX_CACHE_AT) ensure_in_adj(g);
+            }
+            if (cache & GX_CACHE_LCC) {
+                PhaseTimer t(&ctx().timing.build_ms);
+                ensure_lcc_cache(g);
+            }
+            GX_CUDA(cudaStreamSynchronize(ctx().stream));
         } catch (...) {
             delete g;
             throw;

@@ -1,4 +1,6 @@
 // rowplan.cu -- long-row chunk plan (load balancing for power-law degree skew).
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 #include <vector>
 
@@ -19,13 +21,28 @@ __global__ void k_collect_long(const uint64_t *__restrict__ rowptr, uint64_t v0,
     }
 }
 
-__global__ void k_gather_pairs(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ rows, uint64_t count,
-                               uint64_t *__restrict__ pairs)
+// chunks per long row (one extra zero item so that the exclusive scan ends with the total)
+__global__ void k_long_chunk_counts(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ rows, uint64_t count,
+                                    uint32_t *__restrict__ nch)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) { pairs[2 * i] = rowptr[rows[i]]; pairs[2 * i + 1] = rowptr[rows[i] + 1]; }
+    if (i > count) return;
+    nch[i] = i < count ? (uint32_t)((rowptr[rows[i] + 1] - rowptr[rows[i]] + CHUNK - 1) / CHUNK) : 0u;
 }
 
+__global__ void k_fill_chunks(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ rows, uint64_t count,
+                              const uint32_t *__restrict__ first, uint32_t *__restrict__ chunk_row, uint64_t *__restrict__ chunk_begin)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t v = rows[i];
+    const uint64_t a = rowptr[v];
+    const uint32_t f = first[i], k_end = first[i + 1] - f;
+    for (uint32_t k = 0; k < k_end; k++) { chunk_row[f + k] = v; chunk_begin[f + k] = a + (uint64_t)k * CHUNK; }
+}
+
+// Everything stays on the device: long rows are collected in one pass (at most m / ROW_SPLIT of them), sorted
+// by id, their chunk counts scanned; two scalars come back to size the arrays.
 void ensure_plan(Adj &a, uint64_t n)
 {
     RowPlan &p = a.plan;
@@ -34,11 +51,11 @@ void ensure_plan(Adj &a, uint64_t n)
     p.part = make_partition(a.rowptr.p, nullptr, n);
     if (n == 0) { p.built = true; return; }
     const uint64_t v0 = p.part.lo, v1 = p.part.hi;
-    // at most m / ROW_SPLIT rows can be long; size the list by a first counting pass
+    const uint64_t cap = a.col.n / ROW_SPLIT + 1; // a long row has more than ROW_SPLIT entries
     DevBuf<unsigned long long> cnt(1);
     cnt.zero();
-    DevBuf<uint32_t> dummy(1);
-    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, v0, v1, ROW_SPLIT, dummy.p, cnt.p, (uint64_t)0);
+    DevBuf<uint32_t> found(cap);
+    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, v0, v1, ROW_SPLIT, found.p, cnt.p, cap);
     unsigned long long nl = 0;
     read_back(&nl, cnt.p, sizeof(nl));
     p.n_long = nl;
@@ -51,34 +68,23 @@ void ensure_plan(Adj &a, uint64_t n)
         p.built = true;
         return;
     }
-    cnt.zero();
-    GX_LAUNCH(k_collect_long, grid_persistent(8), 256, 0, a.rowptr.p, v0, v1, ROW_SPLIT, p.long_rows.p, cnt.p, (uint64_t)nl);
-    std::vector<uint32_t> rows(nl);
-    GX_CUDA(cudaMemcpyAsync(rows.data(), p.long_rows.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
-    GX_CUDA(cudaStreamSynchronize(ctx().stream));
-    std::sort(rows.begin(), rows.end());
-    // offsets of the long rows only: gathered on the device, one small copy back
-    GX_CUDA(cudaMemcpyAsync(p.long_rows.p, rows.data(), nl * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx().stream));
-    DevBuf<uint64_t> pairs(2 * nl);
-    GX_LAUNCH(k_gather_pairs, grid_for(nl, 256), 256, 0, a.rowptr.p, p.long_rows.p, (uint64_t)nl, pairs.p);
-    std::vector<uint64_t> rp_pairs(2 * nl);
-    GX_CUDA(cudaMemcpyAsync(rp_pairs.data(), pairs.p, 2 * nl * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx().stream));
-    GX_CUDA(cudaStreamSynchronize(ctx().stream));
-    std::vector<uint32_t> first(nl + 1), crow;
-    std::vector<uint64_t> cbeg;
-    for (size_t i = 0; i < nl; i++) {
-        first[i] = (uint32_t)crow.size();
-        for (uint64_t b = rp_pairs[2 * i]; b < rp_pairs[2 * i + 1]; b += CHUNK) { crow.push_back(rows[i]); cbeg.push_back(b); }
+    GX_CUDA(cudaMemcpyAsync(p.long_rows.p, found.p, nl * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx().stream));
+    sort_keys32(p.long_rows, nl, bits_for(n)); // ascending vertex ids whatever order the atomics appended them in
+    GX_LAUNCH(k_long_chunk_counts, grid_for(nl + 1, 256), 256, 0, a.rowptr.p, p.long_rows.p, (uint64_t)nl, p.long_first_chunk.p);
+    {
+        size_t tb = 0;
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, p.long_first_chunk.p, p.long_first_chunk.p, (int64_t)(nl + 1), ctx().stream));
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, p.long_first_chunk.p, p.long_first_chunk.p, (int64_t)(nl + 1), ctx().stream));
+        count_launch();
     }
-    first[nl] = (uint32_t)crow.size();
-    p.n_chunks = crow.size();
-    p.chunk_row.alloc(p.n_chunks);
-    p.chunk_begin.alloc(p.n_chunks);
-    cudaStream_t s = ctx().stream;
-    GX_CUDA(cudaMemcpyAsync(p.long_first_chunk.p, first.data(), (nl + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    GX_CUDA(cudaMemcpyAsync(p.chunk_row.p, crow.data(), p.n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    GX_CUDA(cudaMemcpyAsync(p.chunk_begin.p, cbeg.data(), p.n_chunks * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    GX_CUDA(cudaStreamSynchronize(s)); // host vectors go out of scope
+    uint32_t total = 0;
+    read_back(&total, p.long_first_chunk.p + nl, sizeof(total));
+    p.n_chunks = total;
+    p.chunk_row.alloc(p.n_chunks ? p.n_chunks : 1);
+    p.chunk_begin.alloc(p.n_chunks ? p.n_chunks : 1);
+    GX_LAUNCH(k_fill_chunks, grid_for(nl, 256), 256, 0, a.rowptr.p, p.long_rows.p, (uint64_t)nl, p.long_first_chunk.p, p.chunk_row.p,
+              p.chunk_begin.p);
     p.built = true;
 }
 

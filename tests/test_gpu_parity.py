@@ -227,6 +227,60 @@ def test_sssp_bucket_width_never_changes_a_bit(capi, monkeypatch, delta, light_h
     check_all(capi, rmat.rmat_graph(13, directed=False, weighted=True), what="sssp")
 
 
+def test_pipelined_upload_with_transposition(capi, monkeypatch):
+    """gx_graph_create_csr32_cached(GX_CACHE_AT): the in-edge adjacency is assembled from chunk-local sorted
+    runs while the column ids upload (graph.cu).  Its results must equal the plain path's and the oracle's:
+    BFS (pull levels read A'), PageRank (sums over A' in row order), CDLP (counts over A and A'); also with
+    weights, with jumbled rows, and with an invalid column id in the last chunk."""
+    rng = np.random.default_rng(77)
+    n, m = 60000, 3_000_000                                  # > 2^21 entries: the pipelined path applies
+    hg = csr_from_edges(n, rng.integers(0, n, m), (rng.integers(0, n, m) ** 2 // n), rng.random(m) + 1e-3, True)
+    rp, ci, w = hg.rowptr, hg.colidx, hg.weights
+    T = oracle.transpose(n, rp, ci)
+    src = rmat.max_out_degree_vertex(hg)
+    ref_bfs = oracle.bfs(n, rp, ci, src)
+    ref_pr = oracle.pagerank(n, rp, ci, 0.85, 5, transposed=T)
+    ref_cdlp = oracle.cdlp(n, rp, ci, True, 3, transposed=T)
+    ref_sssp = oracle.sssp(n, rp, ci, w, src)
+
+    def check(g):
+        try:
+            assert np.array_equal(g.bfs(src), ref_bfs)
+            assert rel_err(g.pagerank(0.85, 5), ref_pr) <= PR_TOL
+            assert np.array_equal(g.cdlp(3), ref_cdlp)
+            assert np.array_equal(g.sssp(src), ref_sssp)
+        finally:
+            g.free()
+
+    check(capi.Graph.from_csr(n, rp, ci, w, True, cache=capi.GX_CACHE_AT))
+    monkeypatch.setenv("GX_UPLOAD_PIPELINE", "0")
+    check(capi.Graph.from_csr(n, rp, ci, w, True, cache=capi.GX_CACHE_AT))
+    monkeypatch.delenv("GX_UPLOAD_PIPELINE")
+    # PageRank is bit-identical on both paths: the in-rows list their sources in the same (ascending) order
+    a = capi.Graph.from_csr(n, rp, ci, None, True, cache=capi.GX_CACHE_AT)
+    b = capi.Graph.from_csr(n, rp, ci, None, True)
+    try:
+        assert np.array_equal(a.pagerank(0.85, 10), b.pagerank(0.85, 10))
+    finally:
+        a.free(); b.free()
+    # jumbled rows: every row reversed
+    ci2, w2 = ci.copy(), w.copy()
+    for v in rng.choice(n, 2000, replace=False):
+        lo, hi = int(rp[v]), int(rp[v + 1])
+        ci2[lo:hi] = ci2[lo:hi][::-1]
+        w2[lo:hi] = w2[lo:hi][::-1]
+    check(capi.Graph.from_csr(n, rp, ci2, w2, True, cache=capi.GX_CACHE_AT))
+    # invalid input is rejected, not crashed on
+    bad = ci.copy()
+    bad[-5] = n + 7
+    with pytest.raises(capi.GxError):
+        capi.Graph.from_csr(n, rp, bad, None, True, cache=capi.GX_CACHE_AT)
+    rp_bad = rp.copy()
+    rp_bad[n // 2] = rp_bad[n // 2 + 1] + 3
+    with pytest.raises(capi.GxError):
+        capi.Graph.from_csr(n, rp_bad, ci, None, True, cache=capi.GX_CACHE_AT)
+
+
 def test_lcc_every_apex_size_class(capi):
     """A clique: oriented out-degrees run from 0 to n-1 (long and short lists meet in every
     intersection), and the answer is known in closed form: LCC is exactly 1 everywhere."""
