@@ -323,6 +323,8 @@ struct PtArgs {
     PrScalars sc;
 };
 
+// VAR (experiment switch, GX_PR_VAR): bit 0 = column ids by one 256-bit evict-first load per lane
+template <int VAR>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
     extern __shared__ double s_hot[];
@@ -345,19 +347,16 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
         const uint32_t flags = a.mask[t * 32 + lane]; // bit i: a row starts at entry 8*lane+i
         const uint64_t p0 = B + 8ull * lane;
         uint32_t idx[8];
-        {
-            uint4 x, y;
-            if (p0 + 8 <= E) {
-                x = ld_stream4((const uint4 *)(a.col + p0));
-                y = ld_stream4((const uint4 *)(a.col + p0 + 4));
+        if (p0 + 8 <= E) {
+            if (VAR & 1) {
+                ld_stream8(a.col + p0, idx); // tiles start 1 KB apart in a 256-byte aligned array: 32-byte aligned
             } else {
-                uint32_t tmp[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) tmp[i] = (p0 + i < E) ? ld_stream(a.col + p0 + i) : 0u;
-                x = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
-                y = make_uint4(tmp[4], tmp[5], tmp[6], tmp[7]);
+                const uint4 x = ld_stream4((const uint4 *)(a.col + p0)), y = ld_stream4((const uint4 *)(a.col + p0 + 4));
+                idx[0] = x.x; idx[1] = x.y; idx[2] = x.z; idx[3] = x.w; idx[4] = y.x; idx[5] = y.y; idx[6] = y.z; idx[7] = y.w;
             }
-            idx[0] = x.x; idx[1] = x.y; idx[2] = x.z; idx[3] = x.w; idx[4] = y.x; idx[5] = y.y; idx[6] = y.z; idx[7] = y.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) idx[i] = (p0 + i < E) ? ld_stream(a.col + p0 + i) : 0u;
         }
         const uint32_t k0 = kk & 0x7FFFFFFFu;
         const bool k0_starts_here = (kk >> 31) != 0;   // otherwise row k0 began in an earlier tile
@@ -604,7 +603,10 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
     const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
     const size_t smem = (size_t)hot * sizeof(double);
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int var = 1;
+    if (const char *e = getenv("GX_PR_VAR")) var = atoi(e);
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PrTiles &ptm = *(PrTiles *)g->pr_cache;
     if (!ptm.have_wbuf) {
         peer_alloc(ptm.wbuf[0], pt.slots * sizeof(double));
@@ -681,7 +683,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
-        GX_LAUNCH(k_pr_tiles, g_tiles, PT_WARPS * 32, smem, a);
+        if (var & 1) GX_LAUNCH(k_pr_tiles<1>, g_tiles, PT_WARPS * 32, smem, a);
+        else GX_LAUNCH(k_pr_tiles<0>, g_tiles, PT_WARPS * 32, smem, a);
         if (g_fin && fused)
             GX_LAUNCH(k_pr_tile_fin<true>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
                       n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);

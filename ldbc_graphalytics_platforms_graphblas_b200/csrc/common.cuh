@@ -200,6 +200,14 @@ __device__ __forceinline__ uint4 ld_stream4(const uint4 *p)
                  : "l"(p));
     return v;
 }
+// 8 consecutive ids in one 256-bit load (sm_100), marked evict-first in L2 as well: a read-once
+// stream must not push the gathered vectors out of L2.  p must be 32-byte aligned.
+__device__ __forceinline__ void ld_stream8(const uint32_t *p, uint32_t (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
     double v;

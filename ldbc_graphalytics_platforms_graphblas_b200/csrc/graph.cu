@@ -10,6 +10,7 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -255,6 +256,88 @@ static void upload_common(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t 
     }
 }
 
+// Several GPUs: the transposition is split by COLUMN range.  A rank keeps the (column, row) pairs whose
+// column lies in its 1/nranks slice of the vertices (stable selection), sorts only those, and the
+// sorted slices -- consecutive pieces of the in-edge adjacency -- are all-gathered over NVLink.
+__global__ void k_flag_col_range(const uint32_t *__restrict__ col, uint64_t m, uint32_t lo, uint32_t hi, uint8_t *__restrict__ flag)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < m; e += stride) { const uint32_t c = ld_stream(col + e); flag[e] = (c >= lo && c < hi) ? 1 : 0; }
+}
+
+// rowptr[v] = base + first position in the rank's sorted keys with key >= v, for v in [v_lo, v_hi)
+__global__ void k_rowptr_slice(const uint32_t *__restrict__ keys, uint64_t cnt, uint64_t base, uint64_t v_lo, uint64_t v_hi,
+                               uint64_t *__restrict__ rowptr)
+{
+    uint64_t v = v_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < v_hi; v += stride) {
+        uint64_t lo = 0, hi = cnt;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        rowptr[v] = base + lo;
+    }
+}
+
+static void transpose_partitioned(gx_graph *g)
+{
+    Context &c = ctx();
+    const uint64_t n = g->n, m = g->m;
+    const Partition pv = make_even_partition(n, 32);
+    DevBuf<uint32_t> rows(m);
+    DevBuf<uint8_t> flag(m);
+    expand_row_ids(g->out.rowptr.p, n, m, rows.p);
+    GX_LAUNCH(k_flag_col_range, grid_persistent(8), 256, 0, g->out.col.p, m, (uint32_t)pv.lo, (uint32_t)pv.hi, flag.p);
+    // the selection cannot hold more than m pairs; m / nranks on average -- sized by a first counting pass
+    DevBuf<uint64_t> nsel(1);
+    const uint64_t cap = m;
+    DevBuf<uint32_t> keys(cap), vals(cap);
+    size_t tb = 0, tb2 = 0;
+    GX_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, g->out.col.p, flag.p, keys.p, nsel.p, (int64_t)m, c.stream));
+    {
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, g->out.col.p, flag.p, keys.p, nsel.p, (int64_t)m, c.stream));
+        GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, rows.p, flag.p, vals.p, nsel.p, (int64_t)m, c.stream));
+        count_launch(2);
+    }
+    uint64_t mine = 0;
+    read_back(&mine, nsel.p, sizeof(mine));
+    rows.release();
+    flag.release();
+    // sizes of all slices -> where this rank's slice starts in the in-edge adjacency
+    DevBuf<uint64_t> sizes(c.nranks);
+    GX_CUDA(cudaMemcpyAsync(sizes.p + c.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
+    allgather_equal(sizes.p, Dt::U64, 1);
+    std::vector<uint64_t> hs(c.nranks);
+    read_back(hs.data(), sizes.p, c.nranks * sizeof(uint64_t));
+    Partition pe;
+    pe.b.assign(c.nranks + 1, 0);
+    for (int r = 0; r < c.nranks; r++) pe.b[r + 1] = pe.b[r] + hs[r];
+    pe.lo = pe.b[c.rank];
+    pe.hi = pe.b[c.rank + 1];
+    GX_REQUIRE(pe.b[c.nranks] == m, "transposition slices do not add up");
+    if (mine > 1) {
+        DevBuf<uint32_t> keys_alt(mine), vals_alt(mine);
+        cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p), dv(vals.p, vals_alt.p);
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int64_t)mine, 0, bits_for(n), c.stream));
+        DevBuf<char> tmp(tb2);
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb2, dk, dv, (int64_t)mine, 0, bits_for(n), c.stream));
+        count_launch();
+        if (dk.Current() != keys.p) std::swap(keys.p, keys_alt.p);
+        if (dv.Current() != vals.p) std::swap(vals.p, vals_alt.p);
+        GX_CUDA(cudaStreamSynchronize(c.stream)); // keys_alt / vals_alt are released by scope
+    }
+    if (mine) GX_CUDA(cudaMemcpyAsync(g->in.col.p + pe.lo, vals.p, mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+    if (pv.hi > pv.lo) GX_LAUNCH(k_rowptr_slice, grid_persistent(8), 256, 0, keys.p, mine, pe.lo, pv.lo, pv.hi, g->in.rowptr.p);
+    GX_CUDA(cudaMemcpyAsync(g->in.rowptr.p + n, &m, sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+    allgatherv(g->in.col.p, Dt::U32, pe);
+    allgatherv(g->in.rowptr.p, Dt::U64, pv);
+    GX_CUDA(cudaStreamSynchronize(c.stream)); // &m and the scoped buffers
+}
+
 void ensure_in_adj(gx_graph *g)
 {
     if (!g->directed || g->have_in) return;
@@ -264,6 +347,15 @@ void ensure_in_adj(gx_graph *g)
     g->in.col.alloc(m);
     if (m == 0) {
         g->in.rowptr.zero();
+        g->have_in = true;
+        return;
+    }
+    // splitting pays from 4 ranks on (at 2 the selection passes cost what halving the sort saves);
+    // GX_TRANSPOSE_SPLIT=0 / 1 forces it off / on
+    const char *pe = getenv("GX_TRANSPOSE_SPLIT");
+    const bool split = pe ? pe[0] != '0' : ctx().nranks >= 4;
+    if (multi() && m >= (1ull << 16) && split) {
+        transpose_partitioned(g);
         g->have_in = true;
         return;
     }
@@ -384,7 +476,7 @@ static bool upload_transpose_pipelined(gx_graph *g, uint64_t n, uint64_t nnz, co
     Context &c = ctx();
     if (multi() || n == 0 || nnz < (1ull << 21) || nnz >= 0xFFFFFFFFull) return false;
     if (const char *e = getenv("GX_UPLOAD_PIPELINE")) if (e[0] == '0') return false;
-    // row-block chunks of about equal entry counts, read off the caller's (host) offsets
+    // row-block chunks cut by entry count, read off the caller's (host) offsets
     ChunkBounds cb;
     uint64_t rows[UP_MAX_CHUNKS + 1];
     int K = (int)std::min<uint64_t>(UP_MAX_CHUNKS, nnz >> 20);
@@ -393,7 +485,8 @@ static bool upload_transpose_pipelined(gx_graph *g, uint64_t n, uint64_t nnz, co
     cb.e[0] = 0;
     int kk = 0;
     for (int k = 1; k < K; k++) {
-        const uint64_t target = (uint64_t)(((unsigned __int128)nnz * (unsigned)k) / (unsigned)K);
+        // chunks shrink towards the end: what is left to do after the last byte has arrived is the last chunk's sort
+        const uint64_t target = (uint64_t)((double)nnz * (1.0 - std::pow(1.0 - (double)k / K, 1.6)));
         uint64_t r = (uint64_t)(std::lower_bound(rowptr, rowptr + n + 1, target) - rowptr);
         if (r > n) r = n;
         const uint64_t e = rowptr[r];

@@ -10,6 +10,8 @@ import sys
 import numpy as np
 import torch.distributed as dist
 
+os.environ.setdefault("GX_TRANSPOSE_SPLIT", "1")  # exercise the column-split transposition at any world size
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import oracle  # noqa: E402
