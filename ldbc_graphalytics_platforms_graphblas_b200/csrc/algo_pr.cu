@@ -106,18 +106,22 @@ struct WOut {
     int npeer;                    // 0 on one GPU
 };
 
-// k_pr_tiles takes the destinations by value (kernel parameter space): measured 6 % faster on one GPU than
-// reading the table through a pointer, and no slower on several
+// k_pr_tiles takes the destinations by value (kernel parameter space, no dependent load before the stores)
 struct WOutV {
     double *p[MAX_PEERS];
     int n;
 };
 
+template <bool PEERS>
 __device__ __forceinline__ void w_store_v(const WOutV &o, uint32_t slot, double v)
 {
+    if constexpr (!PEERS) {
+        o.p[0][slot] = v; // one GPU: no predicated-off stores in the instruction stream
+    } else {
 #pragma unroll
-    for (int r = 0; r < MAX_PEERS; r++)
-        if (r < o.n) o.p[r][slot] = v;
+        for (int r = 0; r < MAX_PEERS; r++)
+            if (r < o.n) o.p[r][slot] = v;
+    }
 }
 
 template <bool PEERS>
@@ -215,12 +219,13 @@ __global__ void k_pt_make_pi(const uint32_t *__restrict__ sorted_keys, const uin
     }
 }
 
+// entries beyond `count` pad the last tile: they gather the always-zero slot `zero_slot`
 __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pi, uint64_t count,
-                                   uint32_t *__restrict__ out)
+                                   uint64_t padded, uint32_t zero_slot, uint32_t *__restrict__ out)
 {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; e < count; e += stride) out[e] = pi[col[e]];
+    for (; e < padded; e += stride) out[e] = e < count ? pi[col[e]] : zero_slot;
 }
 
 // w0 in the degree-sorted space (replicated on every rank)
@@ -266,25 +271,27 @@ __global__ void k_pt_slots(const uint32_t *__restrict__ ne_rows, const uint32_t 
     for (; k < K; k += stride) slot_k[k] = pi ? pi[ne_rows[k]] : ne_rows[k];
 }
 
-// per call: d in non-empty-row order, so that a tile's epilogue operands are indexed by k
+// per call: 1 / d in non-empty-row order (0 for a sink), so that a tile's epilogue operands are indexed by k
+// and w' = r * (1/d) costs one multiply instead of an FP64 division sequence (~30 instructions) per row
 __global__ void k_pt_gather_d(const double *__restrict__ d, const uint32_t *__restrict__ ne_rows, uint64_t K,
-                              double *__restrict__ d_k)
+                              double *__restrict__ inv_k)
 {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; k < K; k += stride) d_k[k] = d[ne_rows[k]];
+    for (; k < K; k += stride) { const double dv = d[ne_rows[k]]; inv_k[k] = dv == 0.0 ? 0.0 : 1.0 / dv; }
 }
 
 // epilogue of non-empty row k: r = teleport' + s, w' = r / d, sink mass
+template <bool NO_LOADS, bool PEERS>
 __device__ __forceinline__ void pt_close(uint32_t k, double s, double tele, const double *__restrict__ d_k,
                                          const uint32_t *__restrict__ slot_k, const uint32_t *__restrict__ ne_rows,
                                          const WOutV &w_new, double *__restrict__ rank, double &sink)
 {
     const double r = tele + s;
-    const double dv = d_k[k];
-    const uint32_t slot = slot_k[k];
-    if (dv == 0.0) sink += r;
-    w_store_v(w_new, slot, dv == 0.0 ? 0.0 : r / dv);
+    const double iv = NO_LOADS ? 0.5 : d_k[k]; // 1 / d, 0 for a sink
+    const uint32_t slot = NO_LOADS ? k : slot_k[k];
+    if (iv == 0.0) sink += r;
+    w_store_v<PEERS>(w_new, slot, r * iv);
     if (rank) rank[ne_rows[k]] = r;
 }
 
@@ -323,8 +330,10 @@ struct PtArgs {
     PrScalars sc;
 };
 
-// VAR (experiment switch, GX_PR_VAR): bit 0 = column ids by one 256-bit evict-first load per lane
-template <int VAR>
+// VAR (experiment switch, GX_PR_VAR): 8 = no hot stage in shared memory (all gathers through L1/L2, which
+// then gets the whole 256 KB).  2 and 4 are TIMING DIAGNOSTICS that break the result (tools/pr_ab.py):
+// 2 = epilogue operands not loaded, 4 = no gathers -- what each dependent memory phase of a tile costs.
+template <int VAR, bool PEERS>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
     extern __shared__ double s_hot[];
@@ -333,38 +342,28 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
     const double tele = a.sc.teleport + a.sc.damping * block_sum_ordered(a.sink_in, a.n_sink_in, s_red) / a.sc.n;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.tele_out = tele;
     // the hottest sources (highest out-degree) are read from shared memory instead of through L1/L2
-    for (uint32_t i = threadIdx.x; i < a.hot; i += PT_WARPS * 32) s_hot[i] = a.w[i];
-    __syncthreads();
+    if (!(VAR & 8)) {
+        for (uint32_t i = threadIdx.x; i < a.hot; i += PT_WARPS * 32) s_hot[i] = a.w[i];
+        __syncthreads();
+    }
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
     const uint64_t nwarp = (uint64_t)gridDim.x * PT_WARPS;
     double sink = 0.0;
     for (uint64_t t = (uint64_t)blockIdx.x * PT_WARPS + wib; t < a.n_tiles; t += nwarp) {
-        const uint64_t B = t * PT_TILE;
-        const uint64_t E = (B + PT_TILE < a.M) ? B + PT_TILE : a.M;
         // ---- everything the tile needs is requested at once: first row, row-start bits, column ids
         const uint32_t kk = a.tile_k0[t];
         const uint32_t kk_next = (t + 1 < a.n_tiles) ? a.tile_k0[t + 1] : 0x80000000u;
         const uint32_t flags = a.mask[t * 32 + lane]; // bit i: a row starts at entry 8*lane+i
-        const uint64_t p0 = B + 8ull * lane;
         uint32_t idx[8];
-        if (p0 + 8 <= E) {
-            if (VAR & 1) {
-                ld_stream8(a.col + p0, idx); // tiles start 1 KB apart in a 256-byte aligned array: 32-byte aligned
-            } else {
-                const uint4 x = ld_stream4((const uint4 *)(a.col + p0)), y = ld_stream4((const uint4 *)(a.col + p0 + 4));
-                idx[0] = x.x; idx[1] = x.y; idx[2] = x.z; idx[3] = x.w; idx[4] = y.x; idx[5] = y.y; idx[6] = y.z; idx[7] = y.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) idx[i] = (p0 + i < E) ? ld_stream(a.col + p0 + i) : 0u;
-        }
+        ld_stream8(a.col + t * PT_TILE + 8u * lane, idx); // tiles are whole (padded) and 1 KB apart: 32-byte aligned
         const uint32_t k0 = kk & 0x7FFFFFFFu;
         const bool k0_starts_here = (kk >> 31) != 0;   // otherwise row k0 began in an earlier tile
         const bool ends_here = (kk_next >> 31) != 0;   // a row starts right after this tile (or the block ends)
         // ---- the gathers: 8 independent ones per lane
         double val[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) val[i] = (p0 + i >= E) ? 0.0 : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
+        for (int i = 0; i < 8; i++)
+            val[i] = (VAR & 4) ? (double)idx[i] : (VAR & 8) ? __ldg(a.w + idx[i]) : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
         // rows starting before this lane's first entry (exclusive prefix of the per-lane counts)
         const uint32_t cnt = __popc(flags);
         uint32_t incl = cnt;
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
                 for (int j = 0; j < 8; j++)
                     if ((uint32_t)j >= i0 && (uint32_t)j < i) s += val[j];
                 if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
-                else pt_close(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                else pt_close<(VAR & 2) != 0, PEERS>(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
                 kcur++;
                 i0 = i;
             }
@@ -414,14 +413,14 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
             // the row running into this lane ends at the lane's first row start
             const double tot = carry + head;
             if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
-            else pt_close(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+            else pt_close<(VAR & 2) != 0, PEERS>(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
         }
         if (lane == 31) {
             // the row still open at the end of the tile
             const uint32_t klast = k0 + total_starts;
             const bool began_here = total_starts > 0 || k0_starts_here;
             if (ends_here) {
-                if (began_here) pt_close(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+                if (began_here) pt_close<(VAR & 2) != 0, PEERS>(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
                 else a.head_part[t] = sv;
             } else {
                 if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
@@ -485,8 +484,8 @@ k_pr_tile_fin(const uint32_t *__restrict__ fin_v, const uint32_t *__restrict__ f
             for (uint32_t t = 1; t <= nt; t++) s += head_part[t0 + t];
         }
         const double r = tele + s;
-        if (dv == 0.0) sink += r;
-        w_store<PEERS>(w_new, peers, slot, dv == 0.0 ? 0.0 : r / dv);
+        if (dv == 0.0) sink += r; // dv is 1 / d here, 0 for a sink
+        w_store<PEERS>(w_new, peers, slot, r * dv);
         if (rank) rank[fin_v[i]] = r;
     }
     __shared__ double red[8];
@@ -558,12 +557,16 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         for (int r = 0; r < ctx().nranks; r++) seg = std::max<uint64_t>(seg, in.plan.part.b[r + 1] - in.plan.part.b[r]);
         pt->seg = (seg + 31) & ~31ull;
         pt->slots = pt->seg * (uint64_t)ctx().nranks;
-        GX_REQUIRE(pt->slots < 0xFFFFFFFFull, "vertex slot space exceeds 32 bits");
+        GX_REQUIRE(pt->slots < 0xFFFFFFFEull, "vertex slot space exceeds 32 bits");
         GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->seg, pt->pi.p);
     }
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
-    pt->col.alloc(pt->M ? pt->M : 1);
-    if (pt->M) GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, pt->col.p);
+    // (padded to whole tiles with the index of a slot that always holds 0: the kernel needs no bounds checks)
+    const uint64_t padded = pt->n_tiles * PT_TILE;
+    pt->col.alloc(padded ? padded : 1);
+    if (pt->M)
+        GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, padded, (uint32_t)pt->slots,
+                  pt->col.p);
     pt->tile_k0.alloc(pt->n_tiles ? pt->n_tiles : 1);
     if (pt->n_tiles)
         GX_LAUNCH(k_pt_tile_k0, grid_for(pt->n_tiles, 256), 256, 0, pt->ne_ptr.p, pt->K, pt->n_tiles, pt->tile_k0.p);
@@ -601,21 +604,30 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const uint64_t v0 = plan.part.lo, v1 = plan.part.hi;
     uint32_t hot_cap = PT_HOT;
     if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
-    const uint32_t hot = (uint32_t)(n < hot_cap ? n : hot_cap);
-    const size_t smem = (size_t)hot * sizeof(double);
-    int var = 1;
+    int var = 0;
     if (const char *e = getenv("GX_PR_VAR")) var = atoi(e);
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GX_CUDA(cudaFuncSetAttribute(k_pr_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t hot = (var & 8) ? 0u : (uint32_t)(n < hot_cap ? n : hot_cap);
+    const size_t smem = (size_t)hot * sizeof(double);
+    using TilesFn = void (*)(const PtArgs);
+    static const TilesFn tiles_tab[4][2] = {{k_pr_tiles<0, false>, k_pr_tiles<0, true>}, {k_pr_tiles<2, false>, k_pr_tiles<2, true>},
+                                            {k_pr_tiles<4, false>, k_pr_tiles<4, true>}, {k_pr_tiles<8, false>, k_pr_tiles<8, true>}};
+    const int vi = var == 2 ? 1 : var == 4 ? 2 : var == 8 ? 3 : 0;
+    var = vi == 1 ? 2 : vi == 2 ? 4 : vi == 3 ? 8 : 0;
+    TilesFn tiles_fn[2] = {tiles_tab[vi][0], tiles_tab[vi][1]};
+    GX_CUDA(cudaFuncSetAttribute(tiles_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GX_CUDA(cudaFuncSetAttribute(tiles_fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PrTiles &ptm = *(PrTiles *)g->pr_cache;
     if (!ptm.have_wbuf) {
-        peer_alloc(ptm.wbuf[0], pt.slots * sizeof(double));
-        peer_alloc(ptm.wbuf[1], pt.slots * sizeof(double));
+        peer_alloc(ptm.wbuf[0], (pt.slots + 1) * sizeof(double)); // + the always-zero slot the tile padding gathers
+        peer_alloc(ptm.wbuf[1], (pt.slots + 1) * sizeof(double));
         ptm.have_wbuf = true;
     }
-    // fused exchange (peer stores from the kernels) unless the mapping failed or GX_PR_FUSED=0
+    // fused exchange (peer stores from the kernels) on 2 GPUs -- measured 4 % ahead of the all-gather there, but
+    // 8-byte stores scattered over 7 peers lose to it on 8 GPUs (16.1 vs 10.3 ms per PageRank at RMAT-25);
+    // GX_PR_FUSED=0 / 1 forces it off / on.  Never without the peer mapping.
     const char *fe = getenv("GX_PR_FUSED");
-    const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && !(fe && fe[0] == '0');
+    const bool want_fused = fe ? fe[0] != '0' : c.nranks <= 2;
+    const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && want_fused;
     const uint64_t n_fin = pt.n_span + pt.n_empty;
     DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1), d_fin(n_fin ? n_fin : 1);
     double *wv[2] = {(double *)pt.wbuf[0].local, (double *)pt.wbuf[1].local};
@@ -623,6 +635,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         GX_CUDA(cudaMemsetAsync(wv[0], 0, pt.slots * sizeof(double), c.stream));
         GX_CUDA(cudaMemsetAsync(wv[1], 0, pt.slots * sizeof(double), c.stream));
     }
+    GX_CUDA(cudaMemsetAsync(wv[0] + pt.slots, 0, sizeof(double), c.stream)); // the zero slot (never written)
+    GX_CUDA(cudaMemsetAsync(wv[1] + pt.slots, 0, sizeof(double), c.stream));
     const unsigned g_tiles = (unsigned)c.num_sms;
     const unsigned g_fin = (pt.n_span || pt.n_empty) ? grid_for(pt.n_span + pt.n_empty, 256) : 0;
     const unsigned g_init = grid_persistent(8);
@@ -683,8 +697,14 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
-        if (var & 1) GX_LAUNCH(k_pr_tiles<1>, g_tiles, PT_WARPS * 32, smem, a);
-        else GX_LAUNCH(k_pr_tiles<0>, g_tiles, PT_WARPS * 32, smem, a);
+        {
+            const bool prof__ = profiling();
+            if (prof__) prof_begin("k_pr_tiles");
+            tiles_fn[fused ? 1 : 0]<<<g_tiles, PT_WARPS * 32, smem, c.stream>>>(a);
+            if (prof__) prof_end();
+            count_launch();
+            GX_CUDA(cudaGetLastError());
+        }
         if (g_fin && fused)
             GX_LAUNCH(k_pr_tile_fin<true>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
                       n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
