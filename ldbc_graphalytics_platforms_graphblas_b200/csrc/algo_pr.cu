@@ -308,6 +308,25 @@ __global__ void k_pt_collect_span(const uint64_t *__restrict__ ne_ptr, uint64_t 
     }
 }
 
+// s += v if bit J of m is set -- one predicate-setting logic op and one predicated DADD; written as
+// `if (...) s += v` the compiler selects 0.0 first (two compares, two FSELs and the add per entry)
+template <int J>
+__device__ __forceinline__ void add_if_bit(double &s, double v, uint32_t m)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.f64 %0, %0, %1;\n\t}"
+        : "+d"(s)
+        : "d"(v), "r"(m), "n"(1u << J));
+}
+
+// sum of the lane's values whose positions are set in m, in ascending order
+__device__ __forceinline__ double masked_sum8(const double (&val)[8], uint32_t m)
+{
+    double s = 0.0;
+    add_if_bit<0>(s, val[0], m); add_if_bit<1>(s, val[1], m); add_if_bit<2>(s, val[2], m); add_if_bit<3>(s, val[3], m);
+    add_if_bit<4>(s, val[4], m); add_if_bit<5>(s, val[5], m); add_if_bit<6>(s, val[6], m); add_if_bit<7>(s, val[7], m);
+    return s;
+}
+
 struct PtArgs {
     const uint32_t *col;
     const uint64_t *ne_ptr;
@@ -329,6 +348,83 @@ struct PtArgs {
     uint32_t hot;
     PrScalars sc;
 };
+
+// One 256-entry tile whose 8 values per lane are in registers: row sums from the row-start bits
+// (in-lane pieces, warp segmented scan for rows crossing lanes, head / tail partials for rows crossing
+// tiles) and the fused epilogue r -> w' = r / d, sink mass.
+template <int VAR, bool PEERS>
+__device__ __forceinline__ void pt_tile_rows(const PtArgs &a, uint64_t t, unsigned lane, uint32_t kk, uint32_t kk_next,
+                                             uint32_t flags, const double (&val)[8], double tele, double &sink)
+{
+    const uint32_t k0 = kk & 0x7FFFFFFFu;
+    const bool k0_starts_here = (kk >> 31) != 0;   // otherwise row k0 began in an earlier tile
+    const bool ends_here = (kk_next >> 31) != 0;   // a row starts right after this tile (or the block ends)
+    // rows starting before this lane's first entry (exclusive prefix of the per-lane counts)
+    const uint32_t cnt = __popc(flags);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL, incl, dlt);
+        if (lane >= (unsigned)dlt) incl += up;
+    }
+    const uint32_t before = incl - cnt;
+    const uint32_t total_starts = __shfl_sync(FULL, incl, 31);
+    // ---- rows that end inside the lane: one trip per row start (a tile has ~10, a lane 0..2), so
+    // the epilogue code runs a couple of times per tile instead of once per entry position
+    uint32_t kcur = k0 + before; // row the lane's first entry belongs to
+    uint32_t f = flags, i0 = 0;
+    double head = 0.0;
+    bool seen = false;
+    while (__any_sync(FULL, f != 0)) {
+        if (f) {
+            const uint32_t i = __ffs(f) - 1;
+            f &= f - 1;
+            const double s = masked_sum8(val, ((1u << i) - 1u) & ~((1u << i0) - 1u)); // entries [i0, i)
+            if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
+            else pt_close<(VAR & 2) != 0, PEERS>(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+            kcur++;
+            i0 = i;
+        }
+    }
+    const double acc = masked_sum8(val, 0xFFu & ~((1u << i0) - 1u)); // open sum at the end of the lane: entries [i0, 8)
+    // ---- rows crossing lanes: segmented inclusive scan of the lanes' open sums
+    double sv = acc;
+    bool sf = seen;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const double pv = __shfl_up_sync(FULL, sv, dlt);
+        const int pf = __shfl_up_sync(FULL, (int)sf, dlt);
+        if (lane >= (unsigned)dlt) { if (!sf) sv += pv; sf = sf || pf; }
+    }
+    double carry = __shfl_up_sync(FULL, sv, 1);
+    if (lane == 0) carry = 0.0;
+    if (seen) {
+        // the row running into this lane ends at the lane's first row start
+        const double tot = carry + head;
+        if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
+        else pt_close<(VAR & 2) != 0, PEERS>(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+    }
+    if (lane == 31) {
+        // the row still open at the end of the tile
+        const uint32_t klast = k0 + total_starts;
+        const bool began_here = total_starts > 0 || k0_starts_here;
+        if (ends_here) {
+            if (began_here) pt_close<(VAR & 2) != 0, PEERS>(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
+            else a.head_part[t] = sv;
+        } else {
+            if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
+        }
+    }
+}
+
+// the 8 gathers of a lane: hottest sources from shared memory, the rest through L1/L2
+template <int VAR>
+__device__ __forceinline__ void pt_gather8(const PtArgs &a, const double *s_hot, const uint32_t (&idx)[8], double (&val)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        val[i] = (VAR & 4) ? (double)idx[i] : (VAR & 8) ? __ldg(a.w + idx[i]) : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
+}
 
 // VAR (experiment switch, GX_PR_VAR): 8 = no hot stage in shared memory (all gathers through L1/L2, which
 // then gets the whole 256 KB).  2 and 4 are TIMING DIAGNOSTICS that break the result (tools/pr_ab.py):
@@ -356,76 +452,9 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
         const uint32_t flags = a.mask[t * 32 + lane]; // bit i: a row starts at entry 8*lane+i
         uint32_t idx[8];
         ld_stream8(a.col + t * PT_TILE + 8u * lane, idx); // tiles are whole (padded) and 1 KB apart: 32-byte aligned
-        const uint32_t k0 = kk & 0x7FFFFFFFu;
-        const bool k0_starts_here = (kk >> 31) != 0;   // otherwise row k0 began in an earlier tile
-        const bool ends_here = (kk_next >> 31) != 0;   // a row starts right after this tile (or the block ends)
-        // ---- the gathers: 8 independent ones per lane
         double val[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            val[i] = (VAR & 4) ? (double)idx[i] : (VAR & 8) ? __ldg(a.w + idx[i]) : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
-        // rows starting before this lane's first entry (exclusive prefix of the per-lane counts)
-        const uint32_t cnt = __popc(flags);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const uint32_t up = __shfl_up_sync(FULL, incl, dlt);
-            if (lane >= (unsigned)dlt) incl += up;
-        }
-        const uint32_t before = incl - cnt;
-        const uint32_t total_starts = __shfl_sync(FULL, incl, 31);
-        // ---- rows that end inside the lane: one trip per row start (a tile has ~10, a lane 0..2), so
-        // the epilogue code runs a couple of times per tile instead of once per entry position
-        uint32_t kcur = k0 + before; // row the lane's first entry belongs to
-        uint32_t f = flags, i0 = 0;
-        double head = 0.0;
-        bool seen = false;
-        while (__any_sync(FULL, f != 0)) {
-            if (f) {
-                const uint32_t i = __ffs(f) - 1;
-                f &= f - 1;
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if ((uint32_t)j >= i0 && (uint32_t)j < i) s += val[j];
-                if (!seen) { head = s; seen = true; } // the row running into the lane: closed after the scan
-                else pt_close<(VAR & 2) != 0, PEERS>(kcur, s, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
-                kcur++;
-                i0 = i;
-            }
-        }
-        double acc = 0.0; // open sum at the end of the lane
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if ((uint32_t)j >= i0) acc += val[j];
-        // ---- rows crossing lanes: segmented inclusive scan of the lanes' open sums
-        double sv = acc;
-        bool sf = seen;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const double pv = __shfl_up_sync(FULL, sv, dlt);
-            const int pf = __shfl_up_sync(FULL, (int)sf, dlt);
-            if (lane >= (unsigned)dlt) { if (!sf) sv += pv; sf = sf || pf; }
-        }
-        double carry = __shfl_up_sync(FULL, sv, 1);
-        if (lane == 0) carry = 0.0;
-        if (seen) {
-            // the row running into this lane ends at the lane's first row start
-            const double tot = carry + head;
-            if (before == 0 && !k0_starts_here) a.head_part[t] = tot;
-            else pt_close<(VAR & 2) != 0, PEERS>(k0 + before, tot, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
-        }
-        if (lane == 31) {
-            // the row still open at the end of the tile
-            const uint32_t klast = k0 + total_starts;
-            const bool began_here = total_starts > 0 || k0_starts_here;
-            if (ends_here) {
-                if (began_here) pt_close<(VAR & 2) != 0, PEERS>(klast, sv, tele, a.d_k, a.slot_k, a.ne_rows, a.w_new, a.rank, sink);
-                else a.head_part[t] = sv;
-            } else {
-                if (began_here) a.tail_part[t] = sv; else a.head_part[t] = sv;
-            }
-        }
+        pt_gather8<VAR>(a, s_hot, idx, val); // 8 independent gathers per lane
+        pt_tile_rows<VAR, PEERS>(a, t, lane, kk, kk_next, flags, val, tele, sink);
     }
     __syncthreads();
     sink = warp_sum(sink);
@@ -613,6 +642,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
                                             {k_pr_tiles<4, false>, k_pr_tiles<4, true>}, {k_pr_tiles<8, false>, k_pr_tiles<8, true>}};
     const int vi = var == 2 ? 1 : var == 4 ? 2 : var == 8 ? 3 : 0;
     var = vi == 1 ? 2 : vi == 2 ? 4 : vi == 3 ? 8 : 0;
+    const unsigned tile_threads = PT_WARPS * 32;
     TilesFn tiles_fn[2] = {tiles_tab[vi][0], tiles_tab[vi][1]};
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -700,7 +730,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         {
             const bool prof__ = profiling();
             if (prof__) prof_begin("k_pr_tiles");
-            tiles_fn[fused ? 1 : 0]<<<g_tiles, PT_WARPS * 32, smem, c.stream>>>(a);
+            tiles_fn[fused ? 1 : 0]<<<g_tiles, tile_threads, smem, c.stream>>>(a);
             if (prof__) prof_end();
             count_launch();
             GX_CUDA(cudaGetLastError());
