@@ -347,6 +347,10 @@ struct PtArgs {
     uint64_t K, M, n_tiles;
     uint32_t hot;
     PrScalars sc;
+    // rows without entries (r = teleport'): done by the warps of k_pr_tiles once they run out of tiles
+    const uint32_t *empty_v, *empty_slot;
+    const double *empty_inv;
+    uint64_t n_empty;
 };
 
 // One 256-entry tile whose 8 values per lane are in registers: row sums from the row-start bits
@@ -456,6 +460,14 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
         pt_gather8<VAR>(a, s_hot, idx, val); // 8 independent gathers per lane
         pt_tile_rows<VAR, PEERS>(a, t, lane, kk, kk_next, flags, val, tele, sink);
     }
+    // rows without entries: r = teleport'; a thread each, spread over all warps of the grid (the tail of
+    // the persistent kernel, when the LSU pipe is no longer busy with gathers)
+    for (uint64_t i = ((uint64_t)blockIdx.x * PT_WARPS + wib) * 32 + lane; i < a.n_empty; i += nwarp * 32) {
+        const double iv = a.empty_inv[i];
+        if (iv == 0.0) sink += tele;
+        w_store_v<PEERS>(a.w_new, a.empty_slot[i], tele * iv);
+        if (a.rank) a.rank[a.empty_v[i]] = tele;
+    }
     __syncthreads();
     sink = warp_sum(sink);
     if (lane == 0) s_red[wib] = sink;
@@ -490,7 +502,8 @@ __global__ void k_pt_fin_plan(const uint64_t *__restrict__ ne_ptr, const uint32_
 }
 
 // rows crossing tile borders (tail of the first tile + heads of the next ones, added in tile
-// order) and rows without entries; one thread each, all operands indexed by the thread
+// order); one thread each, all operands indexed by the thread
+constexpr uint32_t FIN_LONG = 32;
 template <bool PEERS>
 __global__ void __launch_bounds__(256)
 k_pr_tile_fin(const uint32_t *__restrict__ fin_v, const uint32_t *__restrict__ fin_slot, const uint32_t *__restrict__ fin_t0,
@@ -502,19 +515,34 @@ k_pr_tile_fin(const uint32_t *__restrict__ fin_v, const uint32_t *__restrict__ f
     const double tele = *tele_p;
     double sink = 0.0;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one row per thread
-    if (i < n_fin) {
-        const double dv = fin_d[i];
-        const uint32_t slot = fin_slot[i];
-        double s = 0.0;
-        if (i < n_span) {
-            const uint32_t t0 = fin_t0[i], nt = fin_nt[i];
-            s = tail_part[t0];
+    const bool live = i < n_fin;
+    uint32_t t0 = 0, nt = 0;
+    double s = 0.0;
+    if (live && i < n_span) {
+        t0 = fin_t0[i];
+        nt = fin_nt[i];
+        s = tail_part[t0];
+        if (nt <= FIN_LONG) {
 #pragma unroll 4
             for (uint32_t t = 1; t <= nt; t++) s += head_part[t0 + t];
         }
+    }
+    // hub rows span hundreds of tiles: the warp adds their partials together (lane-strided loads, then a
+    // fixed-order tree), instead of one thread walking them one dependent load after the other
+    for (unsigned todo = __ballot_sync(FULL, nt > FIN_LONG); todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const uint32_t bt0 = __shfl_sync(FULL, t0, src), bnt = __shfl_sync(FULL, nt, src);
+        double p = 0.0;
+#pragma unroll 4
+        for (uint32_t t = 1 + lane_id(); t <= bnt; t += 32) p += head_part[bt0 + t];
+        p = warp_sum(p);
+        if ((int)lane_id() == src) s += p;
+    }
+    if (live) {
+        const double dv = fin_d[i]; // 1 / d, 0 for a sink
         const double r = tele + s;
-        if (dv == 0.0) sink += r; // dv is 1 / d here, 0 for a sink
-        w_store<PEERS>(w_new, peers, slot, r * dv);
+        if (dv == 0.0) sink += r;
+        w_store<PEERS>(w_new, peers, fin_slot[i], r * dv);
         if (rank) rank[fin_v[i]] = r;
     }
     __shared__ double red[8];
@@ -668,7 +696,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     GX_CUDA(cudaMemsetAsync(wv[0] + pt.slots, 0, sizeof(double), c.stream)); // the zero slot (never written)
     GX_CUDA(cudaMemsetAsync(wv[1] + pt.slots, 0, sizeof(double), c.stream));
     const unsigned g_tiles = (unsigned)c.num_sms;
-    const unsigned g_fin = (pt.n_span || pt.n_empty) ? grid_for(pt.n_span + pt.n_empty, 256) : 0;
+    const unsigned g_fin = pt.n_span ? grid_for(pt.n_span, 256) : 0; // rows without entries ride along in k_pr_tiles
     const unsigned g_init = grid_persistent(8);
     const unsigned nparts = (g_tiles + g_fin > g_init) ? g_tiles + g_fin : g_init;
     DevBuf<double> sinkA(nparts), sinkB(nparts), head_part(pt.n_tiles ? pt.n_tiles : 1), tail_part(pt.n_tiles ? pt.n_tiles : 1);
@@ -727,6 +755,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.rank = rank;
         a.head_part = head_part.p; a.tail_part = tail_part.p; a.sink_out = s_out;
         a.K = pt.K; a.M = pt.M; a.n_tiles = pt.n_tiles; a.hot = hot; a.sc = sc;
+        a.empty_v = pt.fin_v.p + pt.n_span; a.empty_slot = pt.fin_slot.p + pt.n_span; a.empty_inv = d_fin.p + pt.n_span;
+        a.n_empty = pt.n_empty;
         {
             const bool prof__ = profiling();
             if (prof__) prof_begin("k_pr_tiles");
@@ -737,10 +767,10 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         }
         if (g_fin && fused)
             GX_LAUNCH(k_pr_tile_fin<true>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
-                      n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
+                      pt.n_span, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
         else if (g_fin)
             GX_LAUNCH(k_pr_tile_fin<false>, g_fin, 256, 0, pt.fin_v.p, pt.fin_slot.p, pt.fin_t0.p, pt.fin_nt.p, d_fin.p, pt.n_span,
-                      n_fin, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
+                      pt.n_span, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
         if (it + 1 < iters) { if (!fused) allgather_equal(w_new, Dt::F64, pt.seg); }
