@@ -150,6 +150,8 @@ struct PrTiles {
     DevBuf<uint64_t> ne_ptr;    // K+1: local entry offset of its first entry (ne_ptr[0] = 0, ne_ptr[K] = M)
     DevBuf<uint32_t> pi;        // n: vertex -> slot in the index space w lives in (see k_pt_make_pi)
     uint64_t seg = 0, slots = 0; // slots per rank segment (equal, padded), nranks * seg
+    uint32_t hps = 0, hot = 0;   // hot entries per segment / in total (hps * nranks): the stored ids are h < hot for the
+                                 // hottest hps slots of every segment and slot + hot for all others
     PeerBuf wbuf[2];             // the two copies of w (read / written in turn), mapped into all ranks
     bool have_wbuf = false;
     ~PrTiles() { if (have_wbuf) { peer_free(wbuf[0]); peer_free(wbuf[1]); } }
@@ -219,13 +221,22 @@ __global__ void k_pt_make_pi(const uint32_t *__restrict__ sorted_keys, const uin
     }
 }
 
-// entries beyond `count` pad the last tile: they gather the always-zero slot `zero_slot`
+// Stored id of an entry: the hottest `hps` slots of EVERY rank's segment (each segment is sorted by
+// out-degree) get the ids [0, hot) of the shared-memory stage, every other slot is stored as slot + hot,
+// so the kernel's test stays one compare.  Entries beyond `count` pad the last tile: they gather the
+// always-zero slot `zero_slot`.
 __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pi, uint64_t count,
-                                   uint64_t padded, uint32_t zero_slot, uint32_t *__restrict__ out)
+                                   uint64_t padded, uint32_t zero_slot, uint32_t seg, uint32_t hps, uint32_t hot,
+                                   uint32_t *__restrict__ out)
 {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; e < padded; e += stride) out[e] = e < count ? pi[col[e]] : zero_slot;
+    for (; e < padded; e += stride) {
+        uint32_t slot = zero_slot;
+        if (e < count) slot = pi[col[e]];
+        const uint32_t owner = slot / seg, off = slot - owner * seg;
+        out[e] = (slot != zero_slot && off < hps) ? owner * hps + off : slot + hot;
+    }
 }
 
 // w0 in the degree-sorted space (replicated on every rank)
@@ -336,6 +347,8 @@ struct PtArgs {
     const uint32_t *slot_k;
     const double *d_k;
     const double *w;        // degree-sorted space
+    const double *w_cold;   // w - hot: stored ids >= hot are slot + hot
+    uint32_t hps, seg;      // hot entries per rank segment, segment length
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
     double *tele_out;
@@ -427,12 +440,11 @@ __device__ __forceinline__ void pt_gather8(const PtArgs &a, const double *s_hot,
 {
 #pragma unroll
     for (int i = 0; i < 8; i++)
-        val[i] = (VAR & 4) ? (double)idx[i] : (VAR & 8) ? __ldg(a.w + idx[i]) : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w + idx[i]));
+        val[i] = (VAR & 4) ? (double)idx[i] : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w_cold + idx[i]));
 }
 
-// VAR (experiment switch, GX_PR_VAR): 8 = no hot stage in shared memory (all gathers through L1/L2, which
-// then gets the whole 256 KB).  2 and 4 are TIMING DIAGNOSTICS that break the result (tools/pr_ab.py):
-// 2 = epilogue operands not loaded, 4 = no gathers -- what each dependent memory phase of a tile costs.
+// VAR (GX_PR_VAR): 2 and 4 are TIMING DIAGNOSTICS that break the result (tools/pr_ab.py): 2 = epilogue
+// operands not loaded, 4 = no gathers -- what each dependent memory phase of a tile costs.
 template <int VAR, bool PEERS>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
@@ -442,10 +454,11 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
     const double tele = a.sc.teleport + a.sc.damping * block_sum_ordered(a.sink_in, a.n_sink_in, s_red) / a.sc.n;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.tele_out = tele;
     // the hottest sources (highest out-degree) are read from shared memory instead of through L1/L2
-    if (!(VAR & 8)) {
-        for (uint32_t i = threadIdx.x; i < a.hot; i += PT_WARPS * 32) s_hot[i] = a.w[i];
-        __syncthreads();
+    for (uint32_t h = threadIdx.x; h < a.hot; h += PT_WARPS * 32) {
+        const uint32_t owner = h / a.hps;
+        s_hot[h] = a.w[(uint64_t)owner * a.seg + (h - owner * a.hps)]; // one GPU: w[h]
     }
+    __syncthreads();
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
     const uint64_t nwarp = (uint64_t)gridDim.x * PT_WARPS;
     double sink = 0.0;
@@ -614,7 +627,11 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         for (int r = 0; r < ctx().nranks; r++) seg = std::max<uint64_t>(seg, in.plan.part.b[r + 1] - in.plan.part.b[r]);
         pt->seg = (seg + 31) & ~31ull;
         pt->slots = pt->seg * (uint64_t)ctx().nranks;
-        GX_REQUIRE(pt->slots < 0xFFFFFFFEull, "vertex slot space exceeds 32 bits");
+        uint32_t hot_cap = PT_HOT;
+        if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
+        pt->hps = (uint32_t)std::min<uint64_t>(pt->seg, hot_cap / (uint32_t)ctx().nranks);
+        pt->hot = pt->hps * (uint32_t)ctx().nranks;
+        GX_REQUIRE(pt->slots + pt->hot < 0xFFFFFFFEull, "vertex slot space exceeds 32 bits");
         GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->seg, pt->pi.p);
     }
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
@@ -623,7 +640,7 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     pt->col.alloc(padded ? padded : 1);
     if (pt->M)
         GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, padded, (uint32_t)pt->slots,
-                  pt->col.p);
+                  (uint32_t)pt->seg, pt->hps, pt->hot, pt->col.p);
     pt->tile_k0.alloc(pt->n_tiles ? pt->n_tiles : 1);
     if (pt->n_tiles)
         GX_LAUNCH(k_pt_tile_k0, grid_for(pt->n_tiles, 256), 256, 0, pt->ne_ptr.p, pt->K, pt->n_tiles, pt->tile_k0.p);
@@ -659,17 +676,14 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const RowPlan &plan = in.plan;
     const PrTiles &pt = *(PrTiles *)g->pr_cache;
     const uint64_t v0 = plan.part.lo, v1 = plan.part.hi;
-    uint32_t hot_cap = PT_HOT;
-    if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
     int var = 0;
     if (const char *e = getenv("GX_PR_VAR")) var = atoi(e);
-    const uint32_t hot = (var & 8) ? 0u : (uint32_t)(n < hot_cap ? n : hot_cap);
+    const uint32_t hot = pt.hot;
     const size_t smem = (size_t)hot * sizeof(double);
     using TilesFn = void (*)(const PtArgs);
-    static const TilesFn tiles_tab[4][2] = {{k_pr_tiles<0, false>, k_pr_tiles<0, true>}, {k_pr_tiles<2, false>, k_pr_tiles<2, true>},
-                                            {k_pr_tiles<4, false>, k_pr_tiles<4, true>}, {k_pr_tiles<8, false>, k_pr_tiles<8, true>}};
-    const int vi = var == 2 ? 1 : var == 4 ? 2 : var == 8 ? 3 : 0;
-    var = vi == 1 ? 2 : vi == 2 ? 4 : vi == 3 ? 8 : 0;
+    static const TilesFn tiles_tab[3][2] = {{k_pr_tiles<0, false>, k_pr_tiles<0, true>}, {k_pr_tiles<2, false>, k_pr_tiles<2, true>},
+                                            {k_pr_tiles<4, false>, k_pr_tiles<4, true>}};
+    const int vi = var == 2 ? 1 : var == 4 ? 2 : 0;
     const unsigned tile_threads = PT_WARPS * 32;
     TilesFn tiles_fn[2] = {tiles_tab[vi][0], tiles_tab[vi][1]};
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -745,7 +759,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
         double *w_old = wv[cur], *w_new = wv[cur ^ 1];
         const WOut *wout = peer_tab.p + (cur ^ 1);
-        a.w = w_old; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
+        a.w = w_old; a.w_cold = w_old - hot; a.hps = pt.hps ? pt.hps : 1; a.seg = (uint32_t)pt.seg; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
         a.w_new.n = 1;
         a.w_new.p[0] = w_new;
         if (fused) {
