@@ -132,6 +132,24 @@ __device__ __forceinline__ void w_store(double *__restrict__ own, const WOut *__
         for (int r = 0; r < o->npeer; r++) o->peer[r][slot] = v;
 }
 
+// All-gather of w' by peer stores: this rank's finished segment is copied into every peer's buffer with
+// 16-byte loads and stores over NVLink (one launch, no protocol, full-width stores -- unlike the 8-byte
+// scattered stores of the fused path).  Peer p is served by the CTAs with blockIdx.x % npeer == p, so all
+// links are busy at once.  The all-reduce of the sink mass that opens the next iteration is the barrier.
+__global__ void __launch_bounds__(256)
+k_pr_push_segment(const double *__restrict__ own, const WOut *__restrict__ o, uint64_t first, uint64_t count)
+{
+    const int npeer = o->npeer;
+    if (npeer == 0) return;
+    const int p = blockIdx.x % npeer;
+    const unsigned rank_in_peer = blockIdx.x / npeer, ctas_per_peer = gridDim.x / npeer; // gridDim.x is a multiple of npeer
+    const double2 *src = (const double2 *)(own + first); // segments start at multiples of 32 slots: 16-byte aligned
+    double2 *dst = (double2 *)(o->peer[p] + first);
+    const uint64_t n2 = count / 2;
+    for (uint64_t i = (uint64_t)rank_in_peer * 256 + threadIdx.x; i < n2; i += (uint64_t)ctas_per_peer * 256) dst[i] = src[i];
+    if (rank_in_peer == 0 && threadIdx.x == 0 && (count & 1)) o->peer[p][first + count - 1] = own[first + count - 1];
+}
+
 __global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -700,6 +718,9 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const char *fe = getenv("GX_PR_FUSED");
     const bool want_fused = fe ? fe[0] != '0' : c.nranks <= 2;
     const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && want_fused;
+    // otherwise the finished segment is pushed to the peers by one copy kernel (GX_PR_PUSH=0: ncclAllGather)
+    const char *pe = getenv("GX_PR_PUSH");
+    const bool push = multi() && !fused && pt.wbuf[0].shared && pt.wbuf[1].shared && !(pe && pe[0] == '0');
     const uint64_t n_fin = pt.n_span + pt.n_empty;
     DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1), d_fin(n_fin ? n_fin : 1);
     double *wv[2] = {(double *)pt.wbuf[0].local, (double *)pt.wbuf[1].local};
@@ -732,13 +753,13 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         WOut h[2];
         for (int b = 0; b < 2; b++) {
             h[b].npeer = 0;
-            for (int r = 0; fused && r < c.nranks; r++)
+            for (int r = 0; (fused || push) && r < c.nranks; r++)
                 if (r != c.rank) h[b].peer[h[b].npeer++] = (double *)pt.wbuf[b].peer[r];
         }
         GX_CUDA(cudaMemcpyAsync(peer_tab.p, h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
         GX_CUDA(cudaStreamSynchronize(c.stream));
     }
-    if (fused) {
+    if (fused || push) {
         // nobody may store into a rank's buffers before that rank has initialised them
         allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
     }
@@ -787,7 +808,15 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
                       pt.n_span, head_part.p, tail_part.p, tele.p, w_new, wout, rank, s_out + g_tiles);
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
-        if (it + 1 < iters) { if (!fused) allgather_equal(w_new, Dt::F64, pt.seg); }
+        if (it + 1 < iters) {
+            if (push) {
+                const unsigned np = (unsigned)c.nranks - 1;
+                GX_LAUNCH(k_pr_push_segment, np * ((2 * (unsigned)c.num_sms + np - 1) / np), 256, 0, w_new, wout, (uint64_t)c.rank * pt.seg,
+                          pt.seg);
+            } else if (!fused) {
+                allgather_equal(w_new, Dt::F64, pt.seg);
+            }
+        }
         else allgatherv(rank, Dt::F64, plan.part);
         cur ^= 1;
         double *t = s_in; s_in = s_out; s_out = t;

@@ -227,14 +227,17 @@ template <class T>
 static void upload_array(T *dst, const T *src, uint64_t count, Dt dt)
 {
     if (!count) return;
+    cudaStream_t s = ctx().stream;
     if (!multi()) {
-        GX_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+        GX_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
         return;
     }
-    const Partition part = make_even_partition(count, 64);
-    if (part.hi > part.lo)
-        GX_CUDA(cudaMemcpyAsync(dst + part.lo, src + part.lo, (part.hi - part.lo) * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
-    allgatherv(dst, dt, part);
+    // equal slices so that the exchange is ONE ncclAllGather (4x the throughput of a group of broadcasts
+    // with unequal sizes); the few elements beyond nranks * slice are uploaded by every rank
+    const uint64_t nr = (uint64_t)ctx().nranks, per = count / nr / 64 * 64, main = per * nr;
+    if (per) GX_CUDA(cudaMemcpyAsync(dst + ctx().rank * per, src + ctx().rank * per, per * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (count > main) GX_CUDA(cudaMemcpyAsync(dst + main, src + main, (count - main) * sizeof(T), cudaMemcpyHostToDevice, s));
+    allgather_equal(dst, dt, per);
 }
 
 static void upload_common(gx_graph *g, uint64_t n, uint64_t nnz, const uint64_t *rowptr, const double *weights,
@@ -330,10 +333,22 @@ static void transpose_partitioned(gx_graph *g)
         if (dv.Current() != vals.p) std::swap(vals.p, vals_alt.p);
         GX_CUDA(cudaStreamSynchronize(c.stream)); // keys_alt / vals_alt are released by scope
     }
-    if (mine) GX_CUDA(cudaMemcpyAsync(g->in.col.p + pe.lo, vals.p, mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
     if (pv.hi > pv.lo) GX_LAUNCH(k_rowptr_slice, grid_persistent(8), 256, 0, keys.p, mine, pe.lo, pv.lo, pv.hi, g->in.rowptr.p);
     GX_CUDA(cudaMemcpyAsync(g->in.rowptr.p + n, &m, sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
-    allgatherv(g->in.col.p, Dt::U32, pe);
+    {
+        // the slices differ in size: one equal-size ncclAllGather into a padded scratch, then local copies
+        // into place (a group of unequal broadcasts moves the same bytes at a quarter of the throughput)
+        uint64_t slot = 0;
+        for (int r = 0; r < c.nranks; r++) slot = std::max(slot, hs[r]);
+        slot = (slot + 63) / 64 * 64;
+        DevBuf<uint32_t> scratch(slot * (uint64_t)c.nranks);
+        if (mine) GX_CUDA(cudaMemcpyAsync(scratch.p + slot * c.rank, vals.p, mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+        allgather_equal(scratch.p, Dt::U32, slot);
+        for (int r = 0; r < c.nranks; r++)
+            if (hs[r])
+                GX_CUDA(cudaMemcpyAsync(g->in.col.p + pe.b[r], scratch.p + slot * r, hs[r] * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                        c.stream));
+    }
     allgatherv(g->in.rowptr.p, Dt::U64, pv);
     GX_CUDA(cudaStreamSynchronize(c.stream)); // &m and the scoped buffers
 }
