@@ -688,6 +688,58 @@ uint64_t select_flagged(const uint64_t *in, const uint8_t *flags, uint64_t count
     return h;
 }
 
+// table size of an oriented row: 0 below LCC_TAB_MIN entries, else the power of two >= 4 * entries
+__global__ void k_lcc_tab_sizes(const uint64_t *__restrict__ orowptr, uint64_t n, uint64_t per_entry, uint64_t *__restrict__ size)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v <= n; v += stride) {
+        uint64_t sz = 0;
+        if (v < n) {
+            const uint64_t d = orowptr[v + 1] - orowptr[v];
+            if (d >= LCC_TAB_MIN) { sz = 32; while (sz < per_entry * d) sz <<= 1; }
+        }
+        size[v] = sz;
+    }
+}
+
+__global__ void k_lcc_tab_fill(const uint64_t *__restrict__ tab_off, const uint32_t *__restrict__ orow,
+                               const uint32_t *__restrict__ ocol, uint64_t om, uint32_t *__restrict__ tab)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < om; e += stride) {
+        const uint32_t u = orow[e];
+        const uint64_t t0 = tab_off[u], tsz = tab_off[u + 1] - t0;
+        if (!tsz) continue;
+        const uint32_t c = ocol[e];
+        uint64_t s = lcc_tab_hash(c & ~LCC_MULT_BIT, tsz);
+        while (atomicCAS(&tab[t0 + s], 0xFFFFFFFFu, c) != 0xFFFFFFFFu) s = (s + 1) & (tsz - 1);
+    }
+}
+
+// sort key of an oriented entry u -> v: the vertex whose list is the longer one of the intersection
+__global__ void k_lcc_owner_keys(const uint64_t *__restrict__ orowptr, const uint32_t *__restrict__ orow,
+                                 const uint32_t *__restrict__ ocol, uint64_t om, uint32_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < om; e += stride) {
+        const uint32_t u = orow[e], v = ocol[e] & ~LCC_MULT_BIT;
+        const uint64_t du = orowptr[u + 1] - orowptr[u], dv = orowptr[v + 1] - orowptr[v];
+        key[e] = du <= dv ? v : u;
+        idx[e] = (uint32_t)e;
+    }
+}
+
+__global__ void k_lcc_permute(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ orow, const uint32_t *__restrict__ ocol,
+                              uint64_t om, uint32_t *__restrict__ eu, uint32_t *__restrict__ ev)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < om; e += stride) { const uint32_t s = idx[e]; eu[e] = orow[s]; ev[e] = ocol[s]; }
+}
+
 void ensure_lcc_cache(gx_graph *g)
 {
     if (g->have_lcc) return;
@@ -746,6 +798,39 @@ void ensure_lcc_cache(gx_graph *g)
         unsigned long long h = 0;
         read_back(&h, total.p, sizeof(h));
         g->lcc_list_bytes = 4ull * h;
+        // membership tables of the longer rows
+        g->ltab_off.alloc(n + 1);
+        uint64_t per_entry = 4; // slots per entry: load <= 1/4
+        if (const char *e = getenv("GX_LCC_SLOTS")) per_entry = atoi(e) >= 2 ? (uint64_t)atoi(e) : 2; // tuning knob
+        GX_LAUNCH(k_lcc_tab_sizes, grid_persistent(8), 256, 0, g->orowptr.p, n, per_entry, g->ltab_off.p);
+        size_t tb = 0;
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->ltab_off.p, g->ltab_off.p, (int64_t)(n + 1), ctx().stream));
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, g->ltab_off.p, g->ltab_off.p, (int64_t)(n + 1), ctx().stream));
+        uint64_t slots = 0;
+        read_back(&slots, g->ltab_off.p + n, sizeof(slots));
+        g->ltab.alloc(slots ? slots : 1);
+        g->ltab.fill_byte(0xFF);
+        if (slots) GX_LAUNCH(k_lcc_tab_fill, grid_persistent(8), 256, 0, g->ltab_off.p, g->orow.p, g->ocol.p, om, g->ltab.p);
+        // entries ordered by the owner of the longer list (stable: ties stay in (u, v) order)
+        GX_REQUIRE(om < 0xFFFFFFFFull, "LCC needs fewer than 2^32 oriented entries");
+        g->lcc_eu.alloc(om);
+        g->lcc_ev.alloc(om);
+        DevBuf<uint32_t> key(om), key_alt(om), idx(om), idx_alt(om);
+        GX_LAUNCH(k_lcc_owner_keys, grid_persistent(8), 256, 0, g->orowptr.p, g->orow.p, g->ocol.p, om, key.p, idx.p);
+        cub::DoubleBuffer<uint32_t> dk(key.p, key_alt.p), dv(idx.p, idx_alt.p);
+        size_t tb2 = 0;
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int64_t)om, 0, bits_for(n), ctx().stream));
+        DevBuf<char> tmp2(tb2);
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, dk, dv, (int64_t)om, 0, bits_for(n), ctx().stream));
+        GX_LAUNCH(k_lcc_permute, grid_persistent(8), 256, 0, dv.Current(), g->orow.p, g->ocol.p, om, g->lcc_eu.p, g->lcc_ev.p);
+        GX_CUDA(cudaStreamSynchronize(ctx().stream)); // scoped sort buffers
+    } else {
+        g->lcc_eu.alloc(1);
+        g->lcc_ev.alloc(1);
+        g->ltab_off.alloc(n + 1);
+        g->ltab_off.zero();
+        g->ltab.alloc(1);
     }
     g->have_lcc = true;
 }

@@ -38,6 +38,13 @@ struct Adj {
 };
 
 constexpr uint32_t LCC_MULT_BIT = 0x80000000u; // oriented col entry: bit31 = reciprocal pair
+constexpr uint32_t LCC_TAB_MIN = 16;           // oriented rows with at least this many entries get a membership table
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ uint64_t lcc_tab_hash(uint32_t id, uint64_t size_pow2)
+{
+    return ((uint64_t)(id * 2654435761u) * size_pow2) >> 32; // multiplicative hash, top bits
+}
+#endif
 
 // builders shared by graph.cu / rmat.cu
 void expand_row_ids(const uint64_t *rowptr, uint64_t n, uint64_t m, uint32_t *row_of_edge);
@@ -68,6 +75,13 @@ struct gx_graph {
     gx::DevBuf<uint32_t> orow;        // om, source vertex of each oriented entry
     gx::DevBuf<uint32_t> udeg;        // n, degree in U
     uint64_t lcc_list_bytes = 0;      // 4 * sum over oriented edges of (d+(u) + d+(v))
+    // membership tables of the longer oriented rows (open addressing, 4 slots per entry): one or two
+    // probes instead of a binary search when a short list is intersected with a hub's list
+    gx::DevBuf<uint64_t> ltab_off;    // n+1: first slot of row v's table (empty range: no table)
+    gx::DevBuf<uint32_t> ltab;        // slots hold ocol values (id | multiplicity bit), 0xFFFFFFFF = empty
+    // the oriented entries once more, ordered by the owner of the LONGER list of each intersection: the groups
+    // running at any time then probe a handful of tables (L1/L2 hits) instead of thousands (DRAM sectors)
+    gx::DevBuf<uint32_t> lcc_eu, lcc_ev; // om each: source, target | multiplicity bit
 
     void *cdlp_plan = nullptr;        // gx::CdlpPlan (algo_cdlp.cu), degree bins + spill tables
     void *pr_cache = nullptr;         // gx::PrTiles (algo_pr.cu), tiling of the in-edge entries
