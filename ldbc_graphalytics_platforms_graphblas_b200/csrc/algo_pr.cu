@@ -252,7 +252,7 @@ __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint3
     for (; e < padded; e += stride) {
         uint32_t slot = zero_slot;
         if (e < count) slot = pi[col[e]];
-        const uint32_t owner = slot / seg, off = slot - owner * seg;
+        const uint32_t owner = slot < seg ? 0u : slot / seg, off = slot - owner * seg; // (one GPU: no division)
         out[e] = (slot != zero_slot && off < hps) ? owner * hps + off : slot + hot;
     }
 }

@@ -10,7 +10,9 @@
 #include <cub/device/device_select.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -285,14 +287,31 @@ __global__ void k_rowptr_slice(const uint32_t *__restrict__ keys, uint64_t cnt, 
     }
 }
 
+// GX_TIMING_DEBUG=1: wall-clock per phase of the multi-GPU graph construction on stderr (rank 0)
+struct PhaseLog {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseLog() : on(getenv("GX_TIMING_DEBUG") && ctx().rank == 0), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(ctx().stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gx timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static void transpose_partitioned(gx_graph *g)
 {
     Context &c = ctx();
+    PhaseLog pl;
     const uint64_t n = g->n, m = g->m;
     const Partition pv = make_even_partition(n, 32);
     DevBuf<uint32_t> rows(m);
     DevBuf<uint8_t> flag(m);
     expand_row_ids(g->out.rowptr.p, n, m, rows.p);
+    pl.mark("T row ids");
     GX_LAUNCH(k_flag_col_range, grid_persistent(8), 256, 0, g->out.col.p, m, (uint32_t)pv.lo, (uint32_t)pv.hi, flag.p);
     // the selection cannot hold more than m pairs; m / nranks on average -- sized by a first counting pass
     DevBuf<uint64_t> nsel(1);
@@ -308,6 +327,7 @@ static void transpose_partitioned(gx_graph *g)
     }
     uint64_t mine = 0;
     read_back(&mine, nsel.p, sizeof(mine));
+    pl.mark("T select own columns");
     rows.release();
     flag.release();
     // sizes of all slices -> where this rank's slice starts in the in-edge adjacency
@@ -322,6 +342,7 @@ static void transpose_partitioned(gx_graph *g)
     pe.lo = pe.b[c.rank];
     pe.hi = pe.b[c.rank + 1];
     GX_REQUIRE(pe.b[c.nranks] == m, "transposition slices do not add up");
+    pl.mark("T slice sizes");
     if (mine > 1) {
         DevBuf<uint32_t> keys_alt(mine), vals_alt(mine);
         cub::DoubleBuffer<uint32_t> dk(keys.p, keys_alt.p), dv(vals.p, vals_alt.p);
@@ -333,24 +354,38 @@ static void transpose_partitioned(gx_graph *g)
         if (dv.Current() != vals.p) std::swap(vals.p, vals_alt.p);
         GX_CUDA(cudaStreamSynchronize(c.stream)); // keys_alt / vals_alt are released by scope
     }
+    pl.mark("T sort own slice");
     if (pv.hi > pv.lo) GX_LAUNCH(k_rowptr_slice, grid_persistent(8), 256, 0, keys.p, mine, pe.lo, pv.lo, pv.hi, g->in.rowptr.p);
     GX_CUDA(cudaMemcpyAsync(g->in.rowptr.p + n, &m, sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
-    {
+    const char *xe = getenv("GX_TRANSPOSE_XCHG"); // "bcast" / "gather" force one form (tests)
+    const bool by_gather = xe ? xe[0] == 'g' : c.nranks <= 4;
+    if (by_gather) {
         // the slices differ in size: one equal-size ncclAllGather into a padded scratch, then local copies
-        // into place (a group of unequal broadcasts moves the same bytes at a quarter of the throughput)
+        // into place (a group of unequal broadcasts moves the same bytes at a quarter of the throughput).
+        // Measured on 4 GPUs (RMAT-24): 1.4 ms for 1.1 GB.  On 8 GPUs (RMAT-25) the same exchange took 27 ms
+        // and the ranks arrived 16 ms apart (profiles/r1c_dbg_n8_timing.txt) where the grouped broadcasts had
+        // given 29 ms for the whole transposition, so from 5 ranks on the slices go by broadcast.
         uint64_t slot = 0;
         for (int r = 0; r < c.nranks; r++) slot = std::max(slot, hs[r]);
         slot = (slot + 63) / 64 * 64;
         DevBuf<uint32_t> scratch(slot * (uint64_t)c.nranks);
         if (mine) GX_CUDA(cudaMemcpyAsync(scratch.p + slot * c.rank, vals.p, mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+        pl.mark("T scratch alloc + copy");
         allgather_equal(scratch.p, Dt::U32, slot);
+        pl.mark("T all-gather slices");
         for (int r = 0; r < c.nranks; r++)
             if (hs[r])
                 GX_CUDA(cudaMemcpyAsync(g->in.col.p + pe.b[r], scratch.p + slot * r, hs[r] * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
                                         c.stream));
+    } else {
+        if (mine) GX_CUDA(cudaMemcpyAsync(g->in.col.p + pe.lo, vals.p, mine * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+        allgatherv(g->in.col.p, Dt::U32, pe);
+        pl.mark("T broadcast slices");
     }
+    pl.mark("T copies into place");
     allgatherv(g->in.rowptr.p, Dt::U64, pv);
     GX_CUDA(cudaStreamSynchronize(c.stream)); // &m and the scoped buffers
+    pl.mark("T all-gather offsets");
 }
 
 void ensure_in_adj(gx_graph *g)
@@ -960,14 +995,20 @@ extern "C" int gx_graph_create_csr32_cached(gx_graph **out, uint64_t n, uint64_t
             if (g->directed && (cache & GX_CACHE_AT)) // upload with the transposition riding along
                 done = upload_transpose_pipelined(g, n, nnz, rowptr, colidx, weights);
             if (!done) {
+                PhaseLog pl;
                 {
                     PhaseTimer t(&ctx().timing.h2d_ms);
                     upload_common(g, n, nnz, rowptr, weights, directed);
                     upload_array(g->out.col.p, colidx, nnz, Dt::U32);
                 }
-                PhaseTimer t(&ctx().timing.build_ms);
-                finish_graph(g);
-                if (cache & GX_CACHE_AT) ensure_in_adj(g);
+                pl.mark("upload + all-gather");
+                {
+                    PhaseTimer t(&ctx().timing.build_ms);
+                    finish_graph(g);
+                }
+                pl.mark("validation");
+                if (cache & GX_CACHE_AT) ensure_in_adj(g); // (times itself into build_ms)
+                pl.mark("transposition");
             }
             if (cache & GX_CACHE_LCC) {
                 PhaseTimer t(&ctx().timing.build_ms);
