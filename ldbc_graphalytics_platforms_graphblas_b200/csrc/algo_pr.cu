@@ -5,31 +5,39 @@
 //   teleport' = (1-damping)/n + damping/n * sum_{sinks} r,   w = r ./ d,
 //   r = teleport' + A' (plus.second) w.
 //
-// What bounds it on B200 (profiles/r1_microbench_stream_patterns.txt): the 4-byte column ids
-// stream at 5.8 TB/s, but every entry also gathers one 8-byte w[source] at a random address of
-// an L2-resident vector, and an SM resolves one such gather per cycle: 284 G gathers/s, i.e.
-// >= 229 us per iteration for the 65 M entries of RMAT-22, 4.3x the HBM time of the stream.
+// What bounds it on B200: the 4-byte column ids stream at 5.8 TB/s, but every entry also gathers one
+// 8-byte w[source] at a random address, and a load whose 32 lanes hit 32 different cache lines
+// occupies the SM's LSU pipe for 32 cycles (profiles/r1_microbench_stream_patterns.txt: 284 G
+// gathers/s from an L2-resident vector = one per cycle per SM).  With the hottest sources in shared
+// memory (0.27 cycles per gather) a 256-entry tile costs ~195 LSU cycles: >= 175 us per iteration on
+// RMAT-22; the kernel runs at 233 us (DESIGN.md 7 has the experiments that led here).
 //
 // Shape of the kernel.  The entries of the rank's non-empty rows are cut into 256-entry tiles
-// regardless of row borders (RMAT hubs span hundreds of tiles, typical rows a dozen entries).
-// A warp takes a tile; lane L owns the 8 CONSECUTIVE entries [8L, 8L+8): two 16-byte column
-// loads and then 8 independent gathers per lane are in flight before anything is consumed
+// regardless of row borders (RMAT hubs span hundreds of tiles, typical rows a dozen entries); the
+// last tile is padded with the id of a slot that always holds 0, so there are no bounds checks.
+// A warp takes a tile; lane L owns the 8 CONSECUTIVE entries [8L, 8L+8): one 256-bit evict-first
+// column load and then 8 independent gathers per lane are in flight before anything is consumed
 // (the group-per-row shape of the first version kept ~1 in flight and was 27 % slower).  Row
 // borders inside a tile are a precomputed 256-bit mask (one bit per entry that starts a row).
 // A lane closes the rows that start and end among its 8 entries by itself; rows crossing lanes
 // are closed by a warp segmented scan of the lanes' open sums (5 shuffle steps per 256
 // entries); rows crossing tiles leave a head / tail partial per tile that k_pr_tile_fin adds in
-// tile order.  Rows without entries never enter the tiles.  Every sum has a fixed order, so
-// results are bit-reproducible.  w lives in an out-degree-sorted index space (the adjacency copy
-// used here stores pi(source)) whose hottest 24 K entries -- the source of 47 % of RMAT-22's
-// entries -- are staged in shared memory by every CTA.
+// tile order (hub rows: by the warp).  Rows without entries (r = teleport') are done by the warps
+// once they run out of tiles.  The epilogue multiplies by a precomputed 1/d (an FP64 division is
+// ~30 instructions per closed row).  Every sum has a fixed order and the work lists are sorted, so
+// results are bit-reproducible.  w lives in an index space of per-rank segments, each sorted by
+// out-degree; the hottest slots of every segment -- 24 K in total, the source of 47 % of RMAT-22's
+// entries -- are staged in shared memory by every CTA and carry the ids [0, hot) in the stored
+// adjacency copy, all other slots are stored as slot + hot (one compare in the kernel).
 //
 // Kernels per iteration:
 //   k_pr_tiles     persistent, one 1024-thread CTA per SM: teleport' from the previous sink
 //                  partials, hot stage, warp-per-tile gather + segmented sums + fused epilogue
-//                  r -> w' = r/d and sink mass
-//   k_pr_tile_fin  thread per tile-crossing row (ordered sum of its partials) / per empty row
-//   (several GPUs: k_pr_tele + all-reduce of the sink mass; w' goes to all ranks by peer stores)
+//                  r -> w' = r * (1/d) and sink mass, rows without entries in the tail
+//   k_pr_tile_fin  thread per tile-crossing row (sum of its partials)
+//   several GPUs:  k_pr_tele + all-reduce of the sink mass (also the barrier); w' reaches the other ranks
+//                  by peer stores over NVLink -- from the two kernels themselves on 2 GPUs, by one
+//                  copy kernel per iteration (k_pr_push_segment) on more
 // Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>

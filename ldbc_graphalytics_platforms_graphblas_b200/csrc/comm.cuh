@@ -5,6 +5,8 @@
 // blocks balanced by entry count, and the dense per-vertex state is replicated: after each
 // bulk-synchronous step the owned slices are all-gathered (PR ranks, CDLP labels, BFS frontier
 // bitmap) or the replicas min/sum-reduced (WCC parents, SSSP distances, LCC counts).
+// Getting the graph in follows the same idea in reverse: every rank is handed the same host arrays,
+// uploads 1/nranks of them over PCIe and receives the rest by all-gather over NVLink (graph.cu).
 #pragma once
 
 #include <vector>

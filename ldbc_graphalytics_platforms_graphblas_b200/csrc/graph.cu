@@ -3,6 +3,14 @@
 // cudaMalloc/cudaMemcpy block of the reference's cdlp_gpu
 // (cdlp_cuda.cu:181, cdlp_kernel.cu:1162-1196).
 //
+//   one GPU     gx_graph_create_csr32_cached(GX_CACHE_AT): upload in row-block chunks on a copy stream,
+//               every chunk validated / sorted by column while the next one is on the bus, one merge
+//               pass at the end (upload_transpose_pipelined)
+//   several     every rank uploads 1/nranks of the arrays, all-gather over NVLink (upload_array);
+//               transposition split by column range from 4 ranks on (transpose_partitioned)
+//   LCC cache   degree-oriented union graph, membership tables of the longer rows, entries ordered by
+//               the owner of the longer list (ensure_lcc_cache)
+//
 // Construction-time sorting / compaction uses CUB device primitives (CUDA
 // toolkit headers); the per-algorithm hot loops in algo_*.cu are hand-written.
 #include <cub/device/device_radix_sort.cuh>
