@@ -22,3 +22,15 @@ def balanced_bounds(rowptr, nranks, rowptr2=None):
 
 def even_bounds(count, nranks, align=1):
     return [0] + [count * r // nranks // align * align for r in range(1, nranks)] + [count]
+
+
+def upload_slices(count, nranks, align=64):
+    """Mirror of graph.cu upload_array: rank r uploads [r * per, (r + 1) * per) over PCIe, every rank uploads the
+    tail [main, count), and the equal slices are exchanged by one all-gather.  Returns (per, main)."""
+    per = count // nranks // align * align
+    return per, per * nranks
+
+
+def column_slices(n, nranks):
+    """Mirror of graph.cu transpose_partitioned: the vertex (column) range whose in-edges rank r sorts."""
+    return even_bounds(n, nranks, align=32)

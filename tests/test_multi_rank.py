@@ -80,6 +80,86 @@ while frontier.size:
     t = torch.from_numpy(dist_v.copy()); dist.all_reduce(t, op=dist.ReduceOp.MIN); dist_v = t.numpy()
     frontier = np.nonzero(dist_v < prev)[0]
 assert np.array_equal(dist_v, oracle.sssp(n, g.rowptr, g.colidx, g.weights, src)), "partitioned SSSP"
+
+# Transposition split by column range (graph.cu transpose_partitioned): a rank keeps the (column, row) pairs of
+# its vertex slice in row-major order, sorts them stably by column, and the slices concatenate to A'
+cb = partition.column_slices(n, world)
+rows = np.repeat(np.arange(n), np.diff(rp))
+keep = (ci >= cb[rank]) & (ci < cb[rank + 1])
+order = np.argsort(ci[keep], kind="stable")
+my_cols, my_rows = ci[keep][order], rows[keep][order]
+parts = [None] * world
+dist.all_gather_object(parts, (my_cols, my_rows))
+all_cols = np.concatenate([p[0] for p in parts]); all_rows = np.concatenate([p[1] for p in parts])
+assert np.array_equal(all_rows, tci), "column-split transposition: entries"
+assert np.array_equal(np.searchsorted(all_cols, np.arange(n + 1)), trp), "column-split transposition: offsets"
+
+# Upload (graph.cu upload_array): equal slices + a common tail cover the array exactly once
+for count in (0, 5, 64 * world, 64 * world + 3, 1000003):
+    per, main = partition.upload_slices(count, world)
+    got = np.zeros(count, dtype=np.int64)
+    got[rank * per:(rank + 1) * per] += 1            # own PCIe slice
+    t = torch.from_numpy(got); dist.all_reduce(t); got = t.numpy()   # the all-gather
+    got[main:] += 1                                   # tail, uploaded by every rank
+    assert (got == 1).all(), "upload slices"
+
+# CDLP with active rows (algo_cdlp.cu): owners recompute only rows with a changed neighbour, owners mark the
+# neighbours of their changed rows, the maps are OR-ed; labels equal the oracle's after every iteration
+ug = rmat.rmat_graph(10, directed=False)
+un, urp, uci = ug.n, ug.rowptr.astype(np.int64), ug.colidx.astype(np.int64)
+ub = partition.balanced_bounds(urp, world)
+lab = np.arange(un)
+active = np.ones(un, dtype=bool)
+for it in range(1, 9):
+    new = lab.copy()
+    for v in range(ub[rank], ub[rank + 1]):
+        if active[v] and urp[v + 1] > urp[v]:
+            vals, cnts = np.unique(lab[uci[urp[v]:urp[v + 1]]], return_counts=True)
+            new[v] = vals[np.argmax(cnts)]             # smallest label among the most frequent
+    new = allgatherv(new, ub)
+    changed = new != lab
+    mark = np.zeros(un, dtype=np.int64)
+    for v in range(ub[rank], ub[rank + 1]):
+        if changed[v]:
+            mark[uci[urp[v]:urp[v + 1]]] = 1
+    t = torch.from_numpy(mark); dist.all_reduce(t, op=dist.ReduceOp.MAX); active = t.numpy().astype(bool)
+    lab = new
+    assert np.array_equal(lab.astype(np.uint64), oracle.cdlp(un, ug.rowptr, ug.colidx, False, it)), f"active-row CDLP, iteration {it}"
+
+# WCC with the sampled start (algo_wcc.cu): union with the first two entries of every row (replicated), the
+# giant tree S is frozen, only rows outside S are hooked -- both ways per entry -- by their owners
+def find(f, x):
+    while f[x] != x:
+        x = f[x]
+    return x
+f = np.arange(n)
+for r_ in range(2):
+    for u in range(n):
+        if rp[u] + r_ < rp[u + 1]:
+            a, b2 = find(f, u), find(f, ci[rp[u] + r_])
+            if a != b2:
+                f[max(a, b2)] = min(a, b2)
+    f = np.array([find(f, v) for v in range(n)])
+vals, cnts = np.unique(f[(np.arange(1024) * n) // 1024], return_counts=True)
+giant = vals[np.argmax(cnts)]
+rest = np.nonzero(f != giant)[0]
+gp = f.copy()
+while True:
+    before = f.copy()
+    for (ptr, idx, bb) in ((rp, ci, bo), (trp, tci, bo)):
+        for u in rest:
+            if not (bb[rank] <= u < bb[rank + 1]):
+                continue
+            for v in idx[ptr[u]:ptr[u + 1]]:
+                for (x, y) in ((u, v), (v, u)):        # hook both ways: the S side never looks at the edge again
+                    if gp[y] < f[x]:
+                        f[f[x]] = min(f[f[x]], gp[y]); f[x] = min(f[x], gp[y])
+    t = torch.from_numpy(f.copy()); dist.all_reduce(t, op=dist.ReduceOp.MIN); f = t.numpy()
+    f = np.minimum(f, f[f]); gp = f[f]
+    ch = torch.tensor([int((f != before).any())]); dist.all_reduce(ch, op=dist.ReduceOp.MAX)
+    if not int(ch):
+        break
+assert np.array_equal(f.astype(np.uint64), oracle.wcc(n, g.rowptr, g.colidx, True)), "sampled WCC"
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -97,6 +177,8 @@ def test_partition_rule():
         assert loads.max() - loads.min() <= 2 * slack + g.nnz // nr // 4
     assert partition.even_bounds(10, 4) == [0, 2, 5, 7, 10]
     assert partition.even_bounds(100, 2, align=32) == [0, 32, 100]
+    assert partition.upload_slices(1000, 4) == (192, 768) and partition.upload_slices(100, 4) == (0, 0)
+    assert partition.column_slices(100, 2) == [0, 32, 100]
 
 
 def test_world_size_2_gloo_exchange(tmp_path):
