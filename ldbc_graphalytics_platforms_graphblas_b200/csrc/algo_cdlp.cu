@@ -291,10 +291,12 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
                   const uint8_t *__restrict__ ins_side, const uint64_t *__restrict__ ins_begin,
                   const uint64_t *__restrict__ tab_off, const uint64_t *__restrict__ rp0, const uint32_t *__restrict__ col0,
                   const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1, const uint32_t *__restrict__ cur,
-                  const uint8_t *__restrict__ active, uint32_t *__restrict__ gkeys, uint32_t *__restrict__ gcnt)
+                  const uint8_t *__restrict__ active, uint32_t *__restrict__ gkeys, uint32_t *__restrict__ gcnt,
+                  unsigned long long *__restrict__ best_out)
 {
     extern __shared__ uint32_t s_tab[];
     uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
+    __shared__ unsigned long long s_best[8];
     const uint32_t c = blockIdx.x;
     const uint32_t li = ins_row[c];
     const uint32_t v = listL[li];
@@ -317,6 +319,10 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
         warp_insert(key, cnt, CDLP_CT - 1, lab, valid);
     }
     __syncthreads();
+    // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
+    // the row has seen is the row's arg-max: one atomicMax per piece, and the slot-parallel scan of the table
+    // is only needed to clear it (a memset does that when every row is active).
+    unsigned long long best = 0;
     for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) {
         const uint32_t cc = cnt[i];
         if (!cc) continue;
@@ -324,9 +330,26 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
         uint64_t s = ((uint64_t)hash32(lab) * tsize) >> 32;
         for (;;) {
             const uint32_t old = atomicCAS(&gkeys[t0 + s], EMPTY, lab);
-            if (old == EMPTY || old == lab) { atomicAdd(&gcnt[t0 + s], cc); break; }
+            if (old == EMPTY || old == lab) {
+                const unsigned long long now = (unsigned long long)atomicAdd(&gcnt[t0 + s], cc) + cc;
+                const unsigned long long kk = (now << 32) | (uint32_t)~lab;
+                best = kk > best ? kk : best;
+                break;
+            }
             s = (s + 1 == tsize) ? 0 : s + 1;
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long x = __shfl_xor_sync(FULL, best, o);
+        best = x > best ? x : best;
+    }
+    if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; i++) best = s_best[i] > best ? s_best[i] : best;
+        if (best) atomicMax(&best_out[li], best);
     }
 }
 
@@ -637,9 +660,16 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                 } else {
                 if (p.nL) {
                     GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, 256, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
-                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gkeys.p, p.gcnt.p);
-                    GX_LAUNCH(k_cdlp_big_scan, (unsigned)p.n_scan, 256, 0, p.listL.p, p.scan_row.p, p.scan_begin.p, p.tab_off.p, act,
-                              p.gkeys.p, p.gcnt.p, p.best.p);
+                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gkeys.p, p.gcnt.p, p.best.p);
+                    if (!act) {
+                        // every hub row was filled: clearing the tables is two memsets (the scan costs 5 ms per
+                        // iteration while the labels are still many)
+                        p.gkeys.fill_byte(0xFF);
+                        p.gcnt.zero();
+                    } else {
+                        GX_LAUNCH(k_cdlp_big_scan, (unsigned)p.n_scan, 256, 0, p.listL.p, p.scan_row.p, p.scan_begin.p, p.tab_off.p, act,
+                                  p.gkeys.p, p.gcnt.p, p.best.p);
+                    }
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, act, changed);
                 }
                 if (p.nb[5])
