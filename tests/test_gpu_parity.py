@@ -433,3 +433,51 @@ def test_rmat22_size_independent_properties(capi):
         assert rel_err(pr, oracle.pagerank(n, rp, ci, 0.85, 10)) <= PR_TOL
     finally:
         g.free()
+
+
+def test_rmat24_undirected_against_oracle(capi):
+    """BASELINE config [2] at full size: WCC (sampled FastSV) + CDLP (active rows, closed-form first iteration)
+    on the undirected RMAT-24 graph (8.9 M vertices, 521 M stored entries), plus BFS and SSSP (delta-stepping
+    with light/heavy entries) on the same graph -- all bit-exact against the oracle (~25 s of CPU)."""
+    g = capi.Graph.rmat(24, False, weighted=True, want_mapping=False)
+    try:
+        rp, ci, w = g.download()
+        n = g.n
+        src = g.max_degree_vertex()
+        comp = g.wcc()
+        assert np.array_equal(comp, oracle.wcc(n, rp, ci, False)), "wcc"
+        # size-independent properties of the labelling: a label is the smallest id of its component
+        c64 = comp.astype(np.int64)
+        assert (c64 <= np.arange(n)).all() and np.array_equal(c64[c64], c64)
+        assert np.array_equal(g.cdlp(10), oracle.cdlp(n, rp, ci, False, 10)), "cdlp"
+        assert np.array_equal(g.bfs(src), oracle.bfs(n, rp, ci, src)), "bfs"
+        dist = g.sssp(src)
+        assert np.array_equal(dist, oracle.sssp(n, rp, ci, w, src)), "sssp"
+        # fix-point property on a slice of the entries: d(v) <= fl(d(u) + w(u,v))
+        lo, hi = int(rp[n // 2]), int(rp[n // 2 + 200000])
+        rows = np.repeat(np.arange(n // 2, n // 2 + 200000), np.diff(rp[n // 2:n // 2 + 200001].astype(np.int64)))
+        assert (dist[ci[lo:hi].astype(np.int64)] <= dist[rows] + w[lo:hi]).all()
+    finally:
+        g.free()
+
+
+def test_rmat22_undirected_lcc(capi):
+    """BASELINE config [3]: LCC on the undirected RMAT-22 graph (membership tables, owner-ordered entries).
+    The oracle's cost is quadratic in hub degrees, so a random sample of vertices is compared (<= 1e-9 relative);
+    every value must lie in [0, 1] and vertices of degree < 2 must be 0."""
+    g = capi.Graph.rmat(22, False, want_mapping=False)
+    try:
+        rp, ci, _ = g.download()
+        n = g.n
+        out = g.lcc()
+        deg = np.diff(rp.astype(np.int64))
+        assert ((out >= 0.0) & (out <= 1.0)).all() and (out[deg < 2] == 0.0).all()
+        rng = np.random.default_rng(3)
+        cand = rng.integers(0, n, 20000)
+        sample = np.unique(cand[deg[cand] < 2000])[:4000].astype(np.uint64)   # hubs would take minutes on the host
+        ref = oracle.lcc(n, rp, ci, False, subset=sample)
+        idx = sample.astype(np.int64)
+        assert rel_err(out[idx], ref[idx]) <= LCC_TOL
+        assert (out[idx] > 0).sum() > 100, "the sample must exercise non-trivial values"
+    finally:
+        g.free()
