@@ -6,7 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
+#include <exception>
 #include <numeric>
+#include <thread>
 
 #include "computation_timer.hpp"
 
@@ -42,58 +45,109 @@ inline uint64_t parse_u64(const char *&p)
     return v;
 }
 
+// Worker threads of the loader: the text of an RMAT-26 graph is tens of GB, and both the parse and the
+// CSR construction split cleanly (the reference's LAGraph_MMRead is single-threaded, graphio.cpp:14).
+unsigned loader_threads(size_t work_items, size_t min_per_thread)
+{
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("GX_LOADER_THREADS")) t = (unsigned)std::atoi(e);
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    const size_t by_work = work_items / (min_per_thread ? min_per_thread : 1);
+    if (by_work < t) t = by_work ? (unsigned)by_work : 1;
+    return t;
+}
+
+template <class F>
+void run_parallel(unsigned nthreads, F &&body)
+{
+    std::vector<std::exception_ptr> err(nthreads);
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; t++)
+        pool.emplace_back([&, t] { try { body(t); } catch (...) { err[t] = std::current_exception(); } });
+    try { body(0); } catch (...) { err[0] = std::current_exception(); }
+    for (auto &th : pool) th.join();
+    for (auto &e : err)
+        if (e) std::rethrow_exception(e);
+}
+
 // COO (0-based, already mirrored for symmetric files) -> CSR with sorted, duplicate-free rows.
 // Self-loops are dropped and duplicates keep the smallest weight: the algorithms assume a
-// loop-free simple graph (LAGraph_cdlp.c: "assume ... no self edges").
+// loop-free simple graph (LAGraph_cdlp.c: "assume ... no self edges").  Counting, scattering and the
+// per-row sort + dedupe run on all host threads.
 HostMatrix coo_to_csr(GrB_Index n, std::vector<uint32_t> &src, std::vector<uint32_t> &dst, std::vector<double> &val, bool weighted)
 {
     HostMatrix A;
     A.nrows = n;
     A.iso = !weighted;
     const size_t nz = src.size();
+    const unsigned T = loader_threads(nz, 1u << 18);
     std::vector<GrB_Index> cnt(n + 1, 0);
-    for (size_t k = 0; k < nz; k++)
-        if (src[k] != dst[k]) cnt[src[k] + 1]++;
+    run_parallel(T, [&](unsigned t) {
+        for (size_t k = nz * t / T; k < nz * (t + 1) / T; k++)
+            if (src[k] != dst[k]) __atomic_fetch_add(&cnt[src[k] + 1], 1, __ATOMIC_RELAXED);
+    });
     for (GrB_Index i = 0; i < n; i++) cnt[i + 1] += cnt[i];
     std::vector<uint32_t> col(cnt[n]);
     std::vector<double> w(weighted ? cnt[n] : 0);
     {
         std::vector<GrB_Index> cur(cnt.begin(), cnt.end() - 1);
-        for (size_t k = 0; k < nz; k++) {
-            if (src[k] == dst[k]) continue;
-            GrB_Index p = cur[src[k]]++;
-            col[p] = dst[k];
-            if (weighted) w[p] = val[k];
-        }
+        run_parallel(T, [&](unsigned t) {
+            for (size_t k = nz * t / T; k < nz * (t + 1) / T; k++) {
+                if (src[k] == dst[k]) continue;
+                const GrB_Index p = __atomic_fetch_add(&cur[src[k]], 1, __ATOMIC_RELAXED); // any order: rows are sorted below
+                col[p] = dst[k];
+                if (weighted) w[p] = val[k];
+            }
+        });
     }
+    { std::vector<uint32_t>().swap(src); std::vector<uint32_t>().swap(dst); std::vector<double>().swap(val); }
+    // rows sorted by (column, weight) and deduplicated in place, in blocks of rows drawn from a counter
+    std::vector<GrB_Index> kept(n + 1, 0);
+    const unsigned T2 = loader_threads((size_t)n, 1u << 12);
+    std::atomic<GrB_Index> next_block{0};
+    const GrB_Index BLOCK = 4096;
+    run_parallel(T2, [&](unsigned) {
+        std::vector<std::pair<uint32_t, double>> tmp;
+        for (;;) {
+            const GrB_Index r0 = next_block.fetch_add(BLOCK);
+            if (r0 >= n) break;
+            const GrB_Index r1 = std::min<GrB_Index>(n, r0 + BLOCK);
+            for (GrB_Index i = r0; i < r1; i++) {
+                const GrB_Index a = cnt[i], b = cnt[i + 1];
+                GrB_Index out = a;
+                if (weighted) {
+                    tmp.resize(b - a);
+                    for (GrB_Index k = a; k < b; k++) tmp[k - a] = {col[k], w[k]};
+                    std::sort(tmp.begin(), tmp.end());
+                    for (size_t k = 0; k < tmp.size(); k++) {
+                        if (k && tmp[k].first == tmp[k - 1].first) continue; // the smallest weight came first
+                        col[out] = tmp[k].first;
+                        w[out++] = tmp[k].second;
+                    }
+                } else {
+                    std::sort(col.begin() + a, col.begin() + b);
+                    for (GrB_Index k = a; k < b; k++) {
+                        if (k > a && col[k] == col[k - 1]) continue;
+                        col[out++] = col[k];
+                    }
+                }
+                kept[i + 1] = out - a;
+            }
+        }
+    });
     A.Ap.assign(n + 1, 0);
-    A.Aj.reserve(col.size());
-    if (weighted) A.Ax.reserve(col.size());
-    std::vector<uint32_t> perm;
-    for (GrB_Index i = 0; i < n; i++) {
-        const GrB_Index a = cnt[i], b = cnt[i + 1];
-        if (weighted) {
-            perm.resize(b - a);
-            std::iota(perm.begin(), perm.end(), 0u);
-            std::sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) {
-                return col[a + x] != col[a + y] ? col[a + x] < col[a + y] : w[a + x] < w[a + y];
-            });
-            for (size_t k = 0; k < perm.size(); k++) {
-                const uint32_t c = col[a + perm[k]];
-                if (k && c == A.Aj.back() && A.Aj.size() > A.Ap[i]) continue;
-                A.Aj.push_back(c);
-                A.Ax.push_back(w[a + perm[k]]);
-            }
-        } else {
-            std::sort(col.begin() + a, col.begin() + b);
-            for (GrB_Index k = a; k < b; k++) {
-                if (k > a && col[k] == col[k - 1]) continue;
-                A.Aj.push_back(col[k]);
-            }
+    for (GrB_Index i = 0; i < n; i++) A.Ap[i + 1] = A.Ap[i] + kept[i + 1];
+    A.nvals = A.Ap[n];
+    A.Aj.resize(A.nvals);
+    if (weighted) A.Ax.resize(A.nvals);
+    run_parallel(T2, [&](unsigned t) {
+        for (GrB_Index i = n * t / T2; i < n * (t + 1) / T2; i++) {
+            const GrB_Index len = kept[i + 1];
+            std::copy(col.begin() + cnt[i], col.begin() + cnt[i] + len, A.Aj.begin() + A.Ap[i]);
+            if (weighted) std::copy(w.begin() + cnt[i], w.begin() + cnt[i] + len, A.Ax.begin() + A.Ap[i]);
         }
-        A.Ap[i + 1] = A.Aj.size();
-    }
-    A.nvals = A.Aj.size();
+    });
     return A;
 }
 
@@ -121,35 +175,66 @@ HostMatrix ReadMtxFile(const std::string &path)
     if (nrows != ncols) throw std::runtime_error("Adjacency matrix must be square");
     if (nrows >= 0xFFFFFFFEull) throw std::runtime_error("More than 2^32 - 2 vertices are not supported");
     p = next_line(p);
-    std::vector<uint32_t> src, dst;
-    std::vector<double> val;
-    const size_t cap = symmetric ? 2 * nnz : nnz;
-    src.reserve(cap);
-    dst.reserve(cap);
-    if (weighted) val.reserve(cap);
-    for (GrB_Index k = 0; k < nnz; k++) {
-        while (*p == '\n' || *p == '\r' || *p == ' ') p++;
-        if (!*p) throw std::runtime_error("Matrix Market file ends before nnz entries were read");
-        const GrB_Index i = parse_u64(p), j = parse_u64(p);
-        if (i < 1 || j < 1 || i > nrows || j > nrows) throw std::runtime_error("Matrix Market entry out of range");
-        double x = 1.0;
-        if (!pattern) {
-            p = skip_ws(p);
-            char *end = nullptr;
-            x = std::strtod(p, &end);
-            if (end == p) throw std::runtime_error("Matrix Market entry without a value");
-            p = end;
-        }
-        p = next_line(p);
-        src.push_back((uint32_t)(i - 1));
-        dst.push_back((uint32_t)(j - 1));
-        if (weighted) val.push_back(x);
-        if (symmetric && i != j) {
-            src.push_back((uint32_t)(j - 1));
-            dst.push_back((uint32_t)(i - 1));
-            if (weighted) val.push_back(x);
-        }
+    // The body is cut into byte ranges that start at line starts; every thread parses its range into
+    // vectors of its own, which are then copied into place in file order.
+    const char *body = p, *end = file.data.data() + file.data.size() - 1; // (the trailing NUL is not part of the text)
+    const unsigned T = loader_threads((size_t)(end - body), 4u << 20);
+    std::vector<const char *> cut(T + 1);
+    cut[0] = body;
+    cut[T] = end;
+    for (unsigned t = 1; t < T; t++) {
+        const char *q = body + (size_t)(end - body) * t / T;
+        while (q < end && *q != '\n') q++;
+        cut[t] = q < end ? q + 1 : end;
+        if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
+    struct Part { std::vector<uint32_t> src, dst; std::vector<double> val; size_t lines = 0; };
+    std::vector<Part> part(T);
+    run_parallel(T, [&](unsigned t) {
+        Part &o = part[t];
+        const char *q = cut[t], *stop = cut[t + 1];
+        const size_t guess = (size_t)(stop - q) / 12 + 16;
+        o.src.reserve(symmetric ? 2 * guess : guess);
+        o.dst.reserve(symmetric ? 2 * guess : guess);
+        if (weighted) o.val.reserve(symmetric ? 2 * guess : guess);
+        for (;;) {
+            while (q < stop && (*q == '\n' || *q == '\r' || *q == ' ')) q++;
+            if (q >= stop) break;
+            const GrB_Index i = parse_u64(q), j = parse_u64(q);
+            if (i < 1 || j < 1 || i > nrows || j > nrows) throw std::runtime_error("Matrix Market entry out of range");
+            double x = 1.0;
+            if (!pattern) {
+                q = skip_ws(q);
+                char *e = nullptr;
+                x = std::strtod(q, &e);
+                if (e == q) throw std::runtime_error("Matrix Market entry without a value");
+                q = e;
+            }
+            q = next_line(q);
+            o.lines++;
+            o.src.push_back((uint32_t)(i - 1));
+            o.dst.push_back((uint32_t)(j - 1));
+            if (weighted) o.val.push_back(x);
+            if (symmetric && i != j) {
+                o.src.push_back((uint32_t)(j - 1));
+                o.dst.push_back((uint32_t)(i - 1));
+                if (weighted) o.val.push_back(x);
+            }
+        }
+    });
+    size_t lines = 0, total = 0;
+    std::vector<size_t> off(T + 1, 0);
+    for (unsigned t = 0; t < T; t++) { lines += part[t].lines; total += part[t].src.size(); off[t + 1] = total; }
+    if (lines < nnz) throw std::runtime_error("Matrix Market file ends before nnz entries were read");
+    if (lines > nnz) throw std::runtime_error("Matrix Market file holds more entries than its size line announces");
+    std::vector<uint32_t> src(total), dst(total);
+    std::vector<double> val(weighted ? total : 0);
+    run_parallel(T, [&](unsigned t) {
+        std::copy(part[t].src.begin(), part[t].src.end(), src.begin() + off[t]);
+        std::copy(part[t].dst.begin(), part[t].dst.end(), dst.begin() + off[t]);
+        if (weighted) std::copy(part[t].val.begin(), part[t].val.end(), val.begin() + off[t]);
+        Part().src.swap(part[t].src); Part().dst.swap(part[t].dst); Part().val.swap(part[t].val);
+    });
     return coo_to_csr(nrows, src, dst, val, weighted);
 }
 

@@ -101,6 +101,34 @@ def test_relabel_drop_in_matches_reference_format(tmp_path, name):
         assert np.array_equal(h.weights, g.weights)
 
 
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_parallel_mtx_loader_matches_numpy(tmp_path, symmetric, monkeypatch):
+    """The C++ loader parses graph.mtx in byte ranges on all host threads and builds the CSR in parallel
+    (host/graphio.cpp).  A 16 MB weighted file in random line order with repeated entries, self-loops and
+    blank lines must give the same graph.grb with 1 and with 8 threads, equal to the numpy construction
+    (duplicates keep the smallest weight, self-loops are dropped, symmetric files are mirrored)."""
+    rng = np.random.default_rng(5 + symmetric)
+    n, m = 50000, 700000
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    src[:5000], dst[:5000] = src[5000:10000], dst[5000:10000]          # repeated entries with other weights
+    w = np.round(rng.random(m) * 100, 6) + 0.000001
+    (tmp_path / "graph.vtx").write_text("".join(f"{100 + 3 * i}\n" for i in range(n)))
+    lines = [f"{a + 1} {b + 1} {x:.6f}\n" for a, b, x in zip(src, dst, w)]
+    lines[1000] += "\n"                                                 # a blank line inside
+    kind = "symmetric" if symmetric else "general"
+    (tmp_path / "graph.mtx").write_text(f"%%MatrixMarket matrix coordinate real {kind}\n%%GraphBLAS GrB_FP64\n{n} {n} {m}\n" + "".join(lines))
+    assert (tmp_path / "graph.mtx").stat().st_size > 12 << 20           # several 4 MB ranges
+    out = {}
+    for threads in ("1", "8"):
+        monkeypatch.setenv("GX_LOADER_THREADS", threads)
+        subprocess.check_call([os.path.join(EXE, "converter"), "--data-dir", str(tmp_path)], stdout=subprocess.DEVNULL)
+        out[threads] = (tmp_path / "graph.grb").read_bytes()
+    assert out["1"] == out["8"]
+    g = graphio.read_grb(str(tmp_path / "graph.grb"), directed=not symmetric)
+    ref = graphio.csr_from_edges(n, src, dst, np.array([float(f"{x:.6f}") for x in w]), not symmetric)
+    assert np.array_equal(g.rowptr, ref.rowptr) and np.array_equal(g.colidx, ref.colidx) and np.array_equal(g.weights, ref.weights)
+
+
 def test_numpy_grb_writer_matches_cpp_reader_layout(tmp_path):
     g = rmat.rmat_graph(8, directed=True, weighted=True)
     graphio.write_graph_dir(str(tmp_path), g, binary=True)
