@@ -1,36 +1,45 @@
-// computation_timer.hpp -- RAII wall-clock scope timer printing
-// "<name> starts" / "<name> duration: <s>s" to stdout (tab-indented per nesting
-// level, rounded to milliseconds), the log lines the reference's
-// ComputationTimer emits (include/computation_timer.hpp:17-52).
+// computation_timer.hpp -- scope stopwatch of the wrappers: prints "<name> starts" when a phase begins and
+// "<name> duration: <seconds>s" (rounded to milliseconds) when it ends, one tab of indentation per nesting
+// level -- the log lines of the reference's ComputationTimer (include/computation_timer.hpp:17-52), which
+// the harness tees into runner.logs.
 #pragma once
 
-#include <chrono>
+#include <sys/time.h>
+
 #include <cmath>
-#include <iostream>
+#include <cstdio>
 #include <string>
 
 class ComputationTimer {
-    using clock = std::chrono::steady_clock;
-    int level_;
-    std::string name_;
-    clock::time_point t0_;
+    std::string label_;
+    int depth_;
+    double began_; // seconds since the epoch
 
-    void indent() const
+    static double wall()
     {
-        for (int i = 0; i < level_; i++) std::cout << '\t';
+        timeval tv;
+        gettimeofday(&tv, nullptr);
+        return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+    }
+    void say(const char *what, double seconds) const
+    {
+        std::string tabs((size_t)depth_, '\t');
+        if (seconds < 0.0) std::printf("%s%s %s\n", tabs.c_str(), label_.c_str(), what);
+        else std::printf("%s%s %s: %gs\n", tabs.c_str(), label_.c_str(), what, seconds);
+        std::fflush(stdout);
     }
 
   public:
-    explicit ComputationTimer(std::string name, int level = 0) : level_(level), name_(std::move(name)), t0_(clock::now())
+    explicit ComputationTimer(std::string label, int depth = 0) : label_(std::move(label)), depth_(depth), began_(wall())
     {
-        indent();
-        std::cout << name_ << " starts" << std::endl;
+        say("starts", -1.0);
     }
-    ComputationTimer(std::string name, const ComputationTimer &parent) : ComputationTimer(std::move(name), parent.level_ + 1) {}
+    ComputationTimer(std::string label, const ComputationTimer &outer) : ComputationTimer(std::move(label), outer.depth_ + 1) {}
+    ComputationTimer(const ComputationTimer &) = delete;
+    ComputationTimer &operator=(const ComputationTimer &) = delete;
     ~ComputationTimer()
     {
-        const double s = std::chrono::duration<double>(clock::now() - t0_).count();
-        indent();
-        std::cout << name_ << " duration: " << std::round(s * 1000.0) / 1000.0 << "s" << std::endl;
+        const double elapsed = wall() - began_;
+        say("duration", elapsed > 0.0 ? std::round(elapsed * 1000.0) / 1000.0 : 0.0);
     }
 };

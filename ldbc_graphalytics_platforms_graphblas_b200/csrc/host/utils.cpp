@@ -1,44 +1,62 @@
+// utils.cpp -- command-line flags of the per-algorithm binaries and the converter, and the epoch clock behind
+// the "Processing starts/ends at" lines.  Flag semantics are the reference's (src/utils.cpp:19-53): `--key value`
+// pairs in any order, unknown keys skipped, booleans spelled "true".  Table-driven: one row per flag.
 #include "utils.h"
 
-#include <chrono>
+#include <sys/time.h>
+
 #include <cstring>
+
+namespace {
+
+bool spelled_true(const char *text) { return text != nullptr && std::strcmp(text, "true") == 0; }
+
+template <class Params>
+struct FlagRow {
+    const char *name;
+    void (*store)(Params &, const char *);
+};
+
+// Walks argv once; a flag in the very last slot has no value and is skipped rather than read past the array.
+template <class Params, size_t N>
+Params collect(int argc, char **argv, const FlagRow<Params> (&rows)[N])
+{
+    Params out;
+    for (int slot = 1; slot + 1 < argc; ++slot)
+        for (const FlagRow<Params> &row : rows)
+            if (std::strcmp(argv[slot], row.name) == 0) {
+                row.store(out, argv[slot + 1]);
+                break;
+            }
+    return out;
+}
+
+const FlagRow<BenchmarkParameters> kJobFlags[] = {
+    {"--input-dir", [](BenchmarkParameters &b, const char *v) { b.input_dir = v; }},
+    {"--output-file", [](BenchmarkParameters &b, const char *v) { b.output_file = v; }},
+    {"--binary", [](BenchmarkParameters &b, const char *v) { b.binary = spelled_true(v); }},
+    {"--directed", [](BenchmarkParameters &b, const char *v) { b.directed = spelled_true(v); }},
+    {"--source-vertex", [](BenchmarkParameters &b, const char *v) { b.source_vertex = std::stoul(v); }},
+    {"--max-iteration", [](BenchmarkParameters &b, const char *v) { b.max_iteration = std::stoi(v); }},
+    {"--damping-factor", [](BenchmarkParameters &b, const char *v) { b.damping_factor = std::stod(v); }},
+    {"--threadnum", [](BenchmarkParameters &b, const char *v) { b.thread_num = std::stoul(v); }},
+};
+
+const FlagRow<ConverterParameters> kConverterFlags[] = {
+    {"--data-dir", [](ConverterParameters &c, const char *v) { c.data_dir = v; }},
+    {"--weighted", [](ConverterParameters &c, const char *v) { c.weighted = spelled_true(v); }},
+    {"--directed", [](ConverterParameters &c, const char *v) { c.directed = spelled_true(v); }},
+};
+
+} // namespace
+
+BenchmarkParameters ParseBenchmarkParameters(int argc, char **argv) { return collect(argc, argv, kJobFlags); }
+
+ConverterParameters ParseConverterParameters(int argc, char **argv) { return collect(argc, argv, kConverterFlags); }
 
 time_t GetCurrentMilliseconds()
 {
-    using namespace std::chrono;
-    return (time_t)duration_cast<milliseconds>(system_clock::now().time_since_epoch()).count();
-}
-
-static bool is_true(const char *v) { return v && std::strcmp(v, "true") == 0; }
-
-BenchmarkParameters ParseBenchmarkParameters(int argc, char **argv)
-{
-    BenchmarkParameters p;
-    // every argv slot is tried as a key (the reference scans all i, src/utils.cpp:22-50); a key
-    // in the last slot has no value and is ignored instead of reading past argv
-    for (int i = 1; i + 1 < argc; i++) {
-        const std::string key = argv[i];
-        const char *value = argv[i + 1];
-        if (key == "--binary") p.binary = is_true(value);
-        else if (key == "--input-dir") p.input_dir = value;
-        else if (key == "--output-file") p.output_file = value;
-        else if (key == "--directed") p.directed = is_true(value);
-        else if (key == "--source-vertex") p.source_vertex = std::stoul(value);
-        else if (key == "--damping-factor") p.damping_factor = std::stod(value);
-        else if (key == "--max-iteration") p.max_iteration = std::stoi(value);
-        else if (key == "--threadnum") p.thread_num = std::stoul(value);
-    }
-    return p;
-}
-
-ConverterParameters ParseConverterParameters(int argc, char **argv)
-{
-    ConverterParameters p;
-    for (int i = 1; i + 1 < argc; i++) {
-        const std::string key = argv[i];
-        if (key == "--data-dir") p.data_dir = argv[i + 1];
-        else if (key == "--weighted") p.weighted = is_true(argv[i + 1]);
-        else if (key == "--directed") p.directed = is_true(argv[i + 1]);
-    }
-    return p;
+    timeval now;
+    gettimeofday(&now, nullptr);
+    return (time_t)now.tv_sec * 1000 + (time_t)(now.tv_usec / 1000);
 }
