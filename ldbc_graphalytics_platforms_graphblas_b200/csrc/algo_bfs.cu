@@ -256,9 +256,12 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
         Context &c = ctx();
         c.timing = gx_timing{};
         const uint64_t n = g->n, m = g->m;
-        ensure_in_adj(g);
+        // LAGraph's rule (LG_BreadthFirstSearch_SSGrB): pull steps only when the transposed adjacency is
+        // already cached -- a single BFS never pays for a transposition (bfs.cpp:79-80 caches nothing, so the
+        // reference runs push-only).  Undirected graphs pull on the one adjacency they have.
+        const bool can_pull = !g->directed || g->have_in;
         Adj &in = g->in_adj();
-        {
+        if (can_pull) {
             PhaseTimer tb(&c.timing.build_ms);
             ensure_plan(in, n);
         }
@@ -292,7 +295,7 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
                 depth++;
                 m_unvisited = m_unvisited > mf ? m_unvisited - mf : 0;
                 // direction rule (Beamer; LAGraph uses alpha = 8, beta = 500 on the same quantities)
-                if (!pull) { if (mf > m_unvisited / 8 && nf > prev_nf && nf > 1) pull = true; }
+                if (!pull) { if (can_pull && mf > m_unvisited / 8 && nf > prev_nf && nf > 1) pull = true; }
                 else if (nf < n / 500 + 1 && nf < prev_nf) pull = false;
                 prev_nf = nf;
                 cnt.zero();

@@ -138,7 +138,9 @@ extern "C" int gx_lcc(gx_graph *g, double *lcc_host)
             num.zero();
             next_run.zero();
             uint32_t run = LCC_RUN;
-            if (const char *e = getenv("GX_LCC_RUN")) run = (uint32_t)atoi(e) >= 32 ? (uint32_t)atoi(e) : 32; // tuning knob
+            // tuning knob; a multiple of 32 so that the four 8-lane groups of a warp make the same number of trips
+            // (the shuffles inside the trip are warp-wide)
+            if (const char *e = getenv("GX_LCC_RUN")) run = (uint32_t)atoi(e) >= 32 ? ((uint32_t)atoi(e) + 31u) & ~31u : 32;
             // the oriented entry list is split evenly over the ranks; corner counts are summed
             const Partition part = make_even_partition(g->om);
             if (part.hi > part.lo)

@@ -621,6 +621,7 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         read_back(&tail[1], flag.p + (nv - 1), sizeof(uint32_t));
     }
     pt->K = (uint64_t)tail[0] + tail[1];
+    GX_REQUIRE(pt->K < 0x80000000ull, "PageRank tiles need fewer than 2^31 non-empty rows per rank (bit 31 of tile_k0 is a flag)");
     pt->n_empty = nv - pt->K;
     pt->ne_rows.alloc(pt->K ? pt->K : 1);
     pt->ne_ptr.alloc(pt->K + 1);
@@ -769,6 +770,7 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     }
     if (fused || push) {
         // nobody may store into a rank's buffers before that rank has initialised them
+        sink_sum.zero();
         allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
     }
     for (int it = 0; it < iters; it++) {

@@ -54,6 +54,9 @@ __device__ __forceinline__ bool wcc_apply(uint32_t *f, uint32_t u, uint32_t mn)
     return ch;
 }
 
+// BOTH: every entry (u, v) also hooks v with gp(u) -- a directed graph whose in-edge adjacency is not cached is
+// covered by its out-entries alone (an edge of A v A' is stored in at least one of the two rows)
+template <bool BOTH>
 __global__ void __launch_bounds__(256)
 k_wcc_hook(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, uint64_t v0, uint64_t v1,
            const uint32_t *__restrict__ gp, uint32_t *__restrict__ f, int *__restrict__ changed)
@@ -70,8 +73,14 @@ k_wcc_hook(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col
         const bool is_short = live && b > a && (b - a) <= ROW_SPLIT;
         uint32_t mn = 0xFFFFFFFFu;
         if (is_short) {
+            const uint32_t gu = BOTH ? gp[grp] : 0u;
 #pragma unroll 4
-            for (uint64_t e = a + sub; e < b; e += WCC_G) mn = min(mn, gp[ld_stream(col + e)]);
+            for (uint64_t e = a + sub; e < b; e += WCC_G) {
+                const uint32_t v = ld_stream(col + e);
+                const uint32_t gv = gp[v];
+                mn = min(mn, gv);
+                if (BOTH && gu < gv) ch |= wcc_apply(f, v, gu);
+            }
         }
 #pragma unroll
         for (int o = WCC_G / 2; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(FULL, mn, o));
@@ -80,6 +89,7 @@ k_wcc_hook(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col
     if (ch) *changed = 1;
 }
 
+template <bool BOTH>
 __global__ void __launch_bounds__(256)
 k_wcc_hook_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
                  const uint32_t *__restrict__ chunk_row, const uint64_t *__restrict__ chunk_begin,
@@ -91,8 +101,16 @@ k_wcc_hook_chunk(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict
     const uint64_t row_end = rowptr[u + 1];
     const uint64_t e_end = (b0 + CHUNK < row_end) ? b0 + CHUNK : row_end;
     uint32_t mn = 0xFFFFFFFFu;
+    const uint32_t gu = BOTH ? gp[u] : 0u;
+    bool chb = false;
 #pragma unroll 8
-    for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 256) mn = min(mn, gp[ld_stream(col + e)]);
+    for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 256) {
+        const uint32_t v = ld_stream(col + e);
+        const uint32_t gv = gp[v];
+        mn = min(mn, gv);
+        if (BOTH && gu < gv) chb |= wcc_apply(f, v, gu);
+    }
+    if (chb) *changed = 1;
     __shared__ uint32_t red[8];
     mn = warp_min_u32(mn);
     if (lane_id() == 0) red[threadIdx.x >> 5] = mn;
@@ -259,13 +277,20 @@ __global__ void k_widen_u32(const uint32_t *__restrict__ in, uint64_t n, uint64_
     for (; v < n; v += stride) out[v] = in[v];
 }
 
-static void wcc_hook_pass(Adj &a, uint64_t n, const uint32_t *gp, uint32_t *f, int *changed)
+static void wcc_hook_pass(Adj &a, bool both, const uint32_t *gp, uint32_t *f, int *changed)
 {
     const RowPlan &p = a.plan;
+    if (both) {
+        if (p.n_chunks)
+            GX_LAUNCH(k_wcc_hook_chunk<true>, (unsigned)p.n_chunks, 256, 0, a.rowptr.p, a.col.p, p.chunk_row.p, p.chunk_begin.p, gp, f,
+                      changed);
+        GX_LAUNCH(k_wcc_hook<true>, grid_persistent(8), 256, 0, a.rowptr.p, a.col.p, p.part.lo, p.part.hi, gp, f, changed);
+        return;
+    }
     if (p.n_chunks)
-        GX_LAUNCH(k_wcc_hook_chunk, (unsigned)p.n_chunks, 256, 0, a.rowptr.p, a.col.p, p.chunk_row.p, p.chunk_begin.p, gp, f, changed);
-    GX_LAUNCH(k_wcc_hook, grid_persistent(8), 256, 0, a.rowptr.p, a.col.p, p.part.lo, p.part.hi, gp, f, changed);
-    (void)n;
+        GX_LAUNCH(k_wcc_hook_chunk<false>, (unsigned)p.n_chunks, 256, 0, a.rowptr.p, a.col.p, p.chunk_row.p, p.chunk_begin.p, gp, f,
+                  changed);
+    GX_LAUNCH(k_wcc_hook<false>, grid_persistent(8), 256, 0, a.rowptr.p, a.col.p, p.part.lo, p.part.hi, gp, f, changed);
 }
 
 } // namespace gx
@@ -281,11 +306,14 @@ extern "C" int gx_wcc(gx_graph *g, uint64_t *comp_host)
         c.timing = gx_timing{};
         const uint64_t n = g->n;
         if (n == 0) return;
-        ensure_in_adj(g);
+        // A directed graph whose in-edge adjacency is not cached is NOT transposed for this (the reference pays
+        // for A v A' inside its window, wcc.cpp:53-55; a transposition costs more than the whole run here):
+        // every out-entry then hooks both of its ends, which covers A v A' with one pass over A.
+        const bool out_only = g->directed && !g->have_in;
         {
             PhaseTimer tb(&c.timing.build_ms);
             ensure_plan(g->out, n);
-            if (g->directed) ensure_plan(g->in, n);
+            if (g->directed && !out_only) ensure_plan(g->in, n);
         }
         const uint64_t m_sym = g->directed ? 2 * g->m : g->m;
         g->res_u64.alloc(n);
@@ -317,15 +345,16 @@ extern "C" int gx_wcc(gx_graph *g, uint64_t *comp_host)
                 n_rest = h;
                 inspected += 2 * n;
                 all_rows = n_rest > n / 4;
+                if (out_only && n_rest) all_rows = true; // the rest lists need the in-edges of the rest vertices
             }
             for (;;) {
                 if (!all_rows && n_rest == 0) break; // the sample connected everything
                 changed.zero();
                 if (multi()) GX_CUDA(cudaMemcpyAsync(f_prev.p, f.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
                 if (all_rows) {
-                    wcc_hook_pass(g->out, n, gp.p, f.p, changed.p);
-                    if (g->directed) wcc_hook_pass(g->in, n, gp.p, f.p, changed.p);
-                    inspected += m_sym;
+                    wcc_hook_pass(g->out, out_only, gp.p, f.p, changed.p);
+                    if (g->directed && !out_only) wcc_hook_pass(g->in, false, gp.p, f.p, changed.p);
+                    inspected += out_only ? g->m : m_sym;
                 } else {
                     const unsigned grid = grid_for(n_rest * 32, 256) < grid_persistent(8) ? grid_for(n_rest * 32, 256) : grid_persistent(8);
                     GX_LAUNCH(k_wcc_hook_rest, grid, 256, 0, g->out.rowptr.p, g->out.col.p, rest.p, n_rest, part.lo, part.hi, gp.p, f.p,

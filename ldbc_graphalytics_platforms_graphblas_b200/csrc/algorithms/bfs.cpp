@@ -36,7 +36,9 @@ int main(int argc, char **argv)
     }
     const GrB_Index sourceVertex = (GrB_Index)std::distance(mapping.begin(), it);
 
-    gx_graph *G = UploadGraph(A, parameters.directed, GX_CACHE_AT);
+    // as in the reference (bfs.cpp:79-80: neither AT nor the out-degree is cached) nothing derived is built
+    // before the timed window; without a cached A' gx_bfs runs push-only on directed graphs, LAGraph's own rule
+    gx_graph *G = UploadGraph(A, parameters.directed, 0);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     std::vector<int64_t> result = LA_BFS(G, sourceVertex, A.nrows);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

@@ -26,9 +26,10 @@ int main(int argc, char **argv)
     HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
-    // the reference transposes inside its timed window (LAGraph_Cached_AT, pr.cpp:59);
-    // here the in-edge adjacency is part of loading the graph
-    gx_graph *G = UploadGraph(A, parameters.directed, GX_CACHE_AT);
+    // the reference transposes inside its timed window (LAGraph_Cached_AT + Cached_OutDegree, pr.cpp:58-61);
+    // so does gx_pagerank here: the in-edge adjacency and the tile plan are built on first use, between the
+    // two Processing lines
+    gx_graph *G = UploadGraph(A, parameters.directed, 0);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     std::vector<double> result = LA_PR(G, A.nrows, parameters.damping_factor, parameters.max_iteration);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

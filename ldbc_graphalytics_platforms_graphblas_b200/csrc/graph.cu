@@ -484,8 +484,11 @@ __global__ void k_row_heads_range(const uint64_t *__restrict__ rowptr, uint64_t 
 }
 
 // rs[k][c] = first position of column c inside run k (n + 1 offsets per run)
-__global__ void k_sum_runs(const uint64_t *__restrict__ rs, int K, uint64_t n, uint64_t *__restrict__ total)
+// (all three merge kernels leave at once when the validation kernels before them on the stream flagged the input:
+// with a column id >= n the runs are not sorted in the full key and the offsets below would be garbage)
+__global__ void k_sum_runs(const uint64_t *__restrict__ rs, int K, uint64_t n, uint64_t *__restrict__ total, const int *__restrict__ bad)
 {
+    if (*bad) return;
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; c <= n; c += stride) {
@@ -498,8 +501,9 @@ __global__ void k_sum_runs(const uint64_t *__restrict__ rs, int K, uint64_t n, u
 
 // delta[k][c] + (position inside run k) = destination of a run entry with column c
 __global__ void k_run_delta(const uint64_t *__restrict__ in_rowptr, const uint64_t *__restrict__ rs, int K, uint64_t n,
-                            uint64_t *__restrict__ delta)
+                            uint64_t *__restrict__ delta, const int *__restrict__ bad)
 {
+    if (*bad) return;
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; c < n; c += stride) {
@@ -513,8 +517,9 @@ __global__ void k_run_delta(const uint64_t *__restrict__ in_rowptr, const uint64
 }
 
 __global__ void k_merge_runs(const uint32_t *__restrict__ run_keys, const uint32_t *__restrict__ run_vals, const ChunkBounds cb,
-                             const uint64_t *__restrict__ delta, uint64_t n, uint32_t *__restrict__ in_col)
+                             const uint64_t *__restrict__ delta, uint64_t n, uint32_t *__restrict__ in_col, const int *__restrict__ bad)
 {
+    if (*bad) return;
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t m = cb.e[cb.k];
@@ -585,6 +590,8 @@ static bool upload_transpose_pipelined(gx_graph *g, uint64_t n, uint64_t nnz, co
     GX_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb_scan, (uint32_t *)nullptr, (uint32_t *)nullptr, MaxU32(), (int64_t)max_chunk, s));
     GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb_scan64, (uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)(n + 1), s));
     DevBuf<char> tmp(std::max(std::max(tb_sort, tb_scan), tb_scan64));
+    int h[2] = {0, 0};
+    try {
     flags.zero();
     GX_CUDA(cudaEventRecord(ev_t[0], s));
     GX_CUDA(cudaEventRecord(ev_ready, s)); // the copy stream must not touch the buffers before they exist
@@ -613,14 +620,19 @@ static bool upload_transpose_pipelined(gx_graph *g, uint64_t n, uint64_t nnz, co
         rowptr_from_sorted_rows(run_keys.p + e0, cnt, n, runstart.p + (uint64_t)k * (n + 1)); // binary search per column
         count_launch(2);
     }
-    GX_LAUNCH(k_sum_runs, grid_persistent(8), 256, 0, runstart.p, K, n, total.p);
+    GX_LAUNCH(k_sum_runs, grid_persistent(8), 256, 0, runstart.p, K, n, total.p, flags.p);
     GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb_scan64, total.p, g->in.rowptr.p, (int64_t)(n + 1), s));
-    GX_LAUNCH(k_run_delta, grid_persistent(8), 256, 0, g->in.rowptr.p, runstart.p, K, n, delta.p);
-    GX_LAUNCH(k_merge_runs, grid_persistent(8), 256, 0, run_keys.p, run_vals.p, cb, delta.p, n, g->in.col.p);
+    GX_LAUNCH(k_run_delta, grid_persistent(8), 256, 0, g->in.rowptr.p, runstart.p, K, n, delta.p, flags.p);
+    GX_LAUNCH(k_merge_runs, grid_persistent(8), 256, 0, run_keys.p, run_vals.p, cb, delta.p, n, g->in.col.p, flags.p);
     GX_CUDA(cudaStreamWaitEvent(s, ev_ready, 0)); // weights (and everything else on the copy stream)
     GX_CUDA(cudaEventRecord(ev_t[2], s));
-    int h[2] = {0, 0};
     read_back(h, flags.p, sizeof(h));
+    } catch (...) {
+        // the scoped buffers are released on `s`: nothing may still be writing into them from the copy stream
+        cudaStreamSynchronize(copy_stream);
+        cudaStreamSynchronize(s);
+        throw;
+    }
     {
         // h2d_ms: until the last byte arrived; build_ms: what validation + transposition add after it
         float up = 0, all = 0;

@@ -276,28 +276,48 @@ HostMatrix ReadGrbFile(const std::string &path)
         const bool is_hyper = kind == 1, is_sparse = kind == 0 || kind == 2;
         if (fmt != 0 || !(is_hyper || is_sparse)) throw std::runtime_error("Only by-row sparse .grb matrices are supported: " + path);
         if (nrows != ncols) throw std::runtime_error("Adjacency matrix must be square");
-        if (!iso && typecode != 10) throw std::runtime_error("Non-iso .grb values must be FP64: " + path);
+        if (nrows >= 0xFFFFFFFEull) throw std::runtime_error("More than 2^32 - 2 vertices are not supported");
+        // the sizes come from the file: bound them by what the file can hold before allocating
+        {
+            const long here = ftell(f);
+            fseek(f, 0, SEEK_END);
+            const long fsz = ftell(f);
+            fseek(f, here, SEEK_SET);
+            const uint64_t left = fsz > here ? (uint64_t)(fsz - here) : 0;
+            if (nvec > nrows || nvec + 1 > left / 8 || nvals > left / 8 || typesize > 1024)
+                throw std::runtime_error("Corrupt .grb header (sizes exceed the file): " + path);
+        }
         std::vector<GrB_Index> Ap(nvec + 1), Ah, Ai(nvals);
         rd(f, Ap.data(), nvec + 1, path);
         if (is_hyper) { Ah.resize(nvec); rd(f, Ah.data(), nvec, path); }
         rd(f, Ai.data(), nvals, path);
-        A.nrows = nrows;
-        A.nvals = nvals;
-        A.iso = iso;
-        if (!iso) { A.Ax.resize(nvals); rd(f, A.Ax.data(), nvals, path); }
-        A.Ap.assign(nrows + 1, 0);
-        if (is_hyper) {
-            for (uint64_t k = 0; k < nvec; k++) A.Ap[Ah[k] + 1] = Ap[k + 1] - Ap[k];
-            for (uint64_t i = 0; i < nrows; i++) A.Ap[i + 1] += A.Ap[i];
-        } else {
-            if (nvec != nrows) throw std::runtime_error("Sparse .grb with nvec != nrows: " + path);
-            A.Ap = std::move(Ap);
-        }
-        A.Aj.resize(nvals);
-        for (uint64_t k = 0; k < nvals; k++) {
-            if (Ai[k] >= nrows) throw std::runtime_error("Column index out of range in " + path);
-            A.Aj[k] = (uint32_t)Ai[k];
-        }
+        if (Ap[0] != 0 || Ap[nvec] != nvals) throw std::runtime_error("Corrupt .grb offsets (Ap[0] != 0 or Ap[nvec] != nvals): " + path);
+        for (uint64_t k = 0; k < nvec; k++)
+            if (Ap[k] > Ap[k + 1]) throw std::runtime_error("Corrupt .grb offsets (not monotone): " + path);
+        for (uint64_t k = 0; k < nvec && is_hyper; k++)
+            if (Ah[k] >= nrows || (k && Ah[k] <= Ah[k - 1])) throw std::runtime_error("Corrupt .grb row list: " + path);
+        // values: FP64 weights are kept; any other non-iso type (bool / integer dumps of the reference's binwrite)
+        // is skipped and the matrix treated as structural, like an iso one
+        const bool weighted = !iso && typecode == 10 && typesize == 8;
+        std::vector<double> Ax;
+        if (weighted) { Ax.resize(nvals); rd(f, Ax.data(), nvals, path); }
+        // same policy as the .mtx path (coo_to_csr): self-loops dropped, rows sorted, duplicates merged
+        // (smallest weight kept), so both loaders give the same graph for the same data
+        if (!is_hyper && nvec != nrows) throw std::runtime_error("Sparse .grb with nvec != nrows: " + path);
+        std::vector<uint32_t> src(nvals), dst(nvals);
+        const unsigned T = loader_threads((size_t)nvec, 1u << 14);
+        run_parallel(T, [&](unsigned t) {
+            for (uint64_t k = nvec * t / T; k < nvec * (t + 1) / T; k++) {
+                const uint32_t row = (uint32_t)(is_hyper ? Ah[k] : k);
+                for (uint64_t e = Ap[k]; e < Ap[k + 1]; e++) {
+                    if (Ai[e] >= nrows) throw std::runtime_error("Column index out of range in " + path);
+                    src[e] = row;
+                    dst[e] = (uint32_t)Ai[e];
+                }
+            }
+        });
+        { std::vector<GrB_Index>().swap(Ai); std::vector<GrB_Index>().swap(Ap); }
+        A = coo_to_csr(nrows, src, dst, Ax, weighted);
     } catch (...) {
         fclose(f);
         throw;

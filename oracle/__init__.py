@@ -53,6 +53,9 @@ def lib():
         L.oracle_scramble.restype = ctypes.c_uint64
         L.oracle_rmat_edges.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _u64p, _u64p]
         L.oracle_edge_weights.argtypes = [ctypes.c_uint64, _u64p, _u64p, ctypes.c_uint64, _f64p]
+        L.oracle_rmat_csr.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, _u64p, _u64p, _u32p, _u64p,
+                                      ctypes.POINTER(ctypes.c_uint64)]
+        L.oracle_rmat_csr.restype = ctypes.c_int64
         for f in ("oracle_transpose", "oracle_bfs", "oracle_pagerank", "oracle_wcc", "oracle_cdlp",
                   "oracle_lcc", "oracle_sssp"):
             getattr(L, f).restype = ctypes.c_int
@@ -179,3 +182,20 @@ def edge_weights(a, b, seed):
     w = np.empty(a.size, dtype=np.float64)
     lib().oracle_edge_weights(a.size, a, b, int(seed), w)
     return w
+
+
+def rmat_csr(scale, seed, edgefactor=16):
+    """Directed benchmark graph built on all host threads: (n, rowptr, colidx, ids) -- the graph
+    gx_rmat_create builds on the device (used by the CPU reference arm of bench.py)."""
+    nedges = int(edgefactor) << int(scale)
+    N = 1 << int(scale)
+    ids = np.empty(N, dtype=np.uint64)
+    rowptr = np.empty(N + 1, dtype=np.uint64)
+    colidx = np.empty(max(nedges, 1), dtype=np.uint32)
+    scratch = np.empty(2 * max(nedges, 1), dtype=np.uint64)
+    m = ctypes.c_uint64()
+    n = lib().oracle_rmat_csr(int(scale), int(seed), nedges, ids, rowptr, colidx, scratch, ctypes.byref(m))
+    if n < 0:
+        raise RuntimeError(f"oracle rmat_csr failed with {n}")
+    del scratch
+    return int(n), rowptr[: n + 1].copy(), colidx[: m.value].copy(), ids[:n].copy()

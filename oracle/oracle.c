@@ -55,20 +55,48 @@ void oracle_set_threads(int t)
 int oracle_transpose(uint64_t n, const uint64_t *rp, const uint32_t *ci, const double *w,
                      uint64_t *trp, uint32_t *tci, double *tw)
 {
-    uint64_t m = rp[n];
+    /* Parallel and still stable (SuiteSparse's own transpose is an OpenMP bucket sort, so a serial
+     * one would sandbag the CPU baseline): (1) column counts with atomic increments, (2) prefix sum,
+     * (3) the columns are cut into one range per thread, balanced by entry count; every thread walks
+     * ALL rows in order and scatters only the entries whose column lies in its range, so inside a
+     * column the rows stay ascending and no two threads touch the same cursor. */
+    const uint64_t m = rp[n];
     memset(trp, 0, (n + 1) * sizeof(uint64_t));
-    for (uint64_t e = 0; e < m; e++) trp[(uint64_t)ci[e] + 1]++;
+#pragma omp parallel for schedule(static)
+    for (uint64_t e = 0; e < m; e++) __atomic_fetch_add(&trp[(uint64_t)ci[e] + 1], 1, __ATOMIC_RELAXED);
     for (uint64_t i = 0; i < n; i++) trp[i + 1] += trp[i];
     uint64_t *cur = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
     if (!cur) return -1;
     memcpy(cur, trp, (n + 1) * sizeof(uint64_t));
-    for (uint64_t i = 0; i < n; i++) {
-        for (uint64_t e = rp[i]; e < rp[i + 1]; e++) {
-            uint64_t p = cur[ci[e]]++;
-            tci[p] = (uint32_t)i;
-            if (w && tw) tw[p] = w[e];
+    int nt = oracle_num_threads();
+    if (nt < 1) nt = 1;
+    if ((uint64_t)nt > n) nt = n ? (int)n : 1;
+    uint64_t *cut = (uint64_t *)malloc(((size_t)nt + 1) * sizeof(uint64_t));
+    if (!cut) { free(cur); return -1; }
+    cut[0] = 0;
+    for (int t = 1; t < nt; t++) {
+        /* first column c with trp[c] >= t * m / nt */
+        const uint64_t target = (uint64_t)(((__uint128_t)m * (uint64_t)t) / (uint64_t)nt);
+        uint64_t lo = cut[t - 1], hi = n;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (trp[mid] < target) lo = mid + 1; else hi = mid; }
+        cut[t] = lo;
+    }
+    cut[nt] = n;
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+    for (int t = 0; t < nt; t++) {
+        const uint64_t c0 = cut[t], c1 = cut[t + 1];
+        if (c0 >= c1) continue;
+        for (uint64_t i = 0; i < n; i++) {
+            for (uint64_t e = rp[i]; e < rp[i + 1]; e++) {
+                const uint64_t c = ci[e];
+                if (c < c0 || c >= c1) continue;
+                const uint64_t p = cur[c]++;
+                tci[p] = (uint32_t)i;
+                if (w && tw) tw[p] = w[e];
+            }
         }
     }
+    free(cut);
     free(cur);
     return 0;
 }
@@ -336,7 +364,8 @@ int oracle_lcc(uint64_t n, const uint64_t *rp, const uint32_t *ci,
         uint64_t cap = 64;
         uint32_t *nb = (uint32_t *)malloc(cap * sizeof(uint32_t));
         if (!mark || !nb) err = 1;
-#pragma omp for schedule(dynamic, 64)
+        /* small chunks: one hub costs as much as thousands of ordinary vertices, and a subset may hold several */
+#pragma omp for schedule(dynamic, 4)
         for (uint64_t k = 0; k < total; k++) {
             if (err) continue;
             uint64_t v = subset ? subset[k] : k;
@@ -501,4 +530,113 @@ void oracle_edge_weights(uint64_t count, const uint64_t *a, const uint64_t *b, u
 {
 #pragma omp parallel for schedule(static)
     for (uint64_t k = 0; k < count; k++) w[k] = oracle_edge_weight(a[k], b[k], seed);
+}
+
+/* ------------------------------------------------------------------------
+ * Host-side construction of the benchmark graph for the CPU reference arm
+ * (bench.py --impl reference), on all host threads: the same graph as the device
+ * generator (csrc/rmat.cu) -- self-loops and duplicate edges dropped, isolated ids
+ * removed, dense id = rank of the scrambled id, directed.  numpy's single-threaded sort
+ * of the 2^(scale+4) keys took minutes from scale 24 on.
+ * Caller-allocated: ids[2^scale], rowptr[2^scale + 1], colidx[ef * 2^scale],
+ * scratch[2 * ef * 2^scale] (uint64).  Returns n (dense vertices), *m_out = entries; < 0 on error.
+ * ---------------------------------------------------------------------- */
+static int cmp_u64(const void *a, const void *b)
+{
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return (x > y) - (x < y);
+}
+
+int64_t oracle_rmat_csr(int scale, uint64_t seed, uint64_t nedges, uint64_t *ids, uint64_t *rowptr,
+                        uint32_t *colidx, uint64_t *scratch, uint64_t *m_out)
+{
+    if (scale < 1 || scale > 31) return -2;
+    const uint64_t N = 1ull << scale;
+    uint64_t *keys = scratch, *tmp = scratch + nedges;
+    uint8_t *present = (uint8_t *)calloc(N, 1);
+    uint32_t *lut = (uint32_t *)malloc(N * sizeof(uint32_t));
+    if (!present || !lut) { free(present); free(lut); return -1; }
+    /* edges as (src << 32 | dst) of scrambled ids; tmp holds the dst half during generation */
+    oracle_rmat_edges(scale, seed, 0, nedges, keys, tmp);
+#pragma omp parallel for schedule(static)
+    for (uint64_t k = 0; k < nedges; k++) {
+        const uint64_t s = keys[k], d = tmp[k];
+        if (s != d) { present[s] = 1; present[d] = 1; } /* benign: every writer stores 1 */
+        keys[k] = (s << 32) | d;
+    }
+    uint64_t n = 0;
+    for (uint64_t v = 0; v < N; v++)
+        if (present[v]) { lut[v] = (uint32_t)n; ids[n++] = v; }
+    free(present);
+    /* dense keys; self-loops become the sentinel (sorts last) */
+#pragma omp parallel for schedule(static)
+    for (uint64_t k = 0; k < nedges; k++) {
+        const uint64_t s = keys[k] >> 32, d = keys[k] & 0xFFFFFFFFull;
+        keys[k] = (s == d) ? ~0ull : (((uint64_t)lut[s] << 32) | lut[d]);
+    }
+    free(lut);
+    /* bucket sort by the top bits of the dense source id, then qsort inside the buckets */
+    int nb_bits = 12;
+    int id_bits = 1;
+    while (id_bits < 32 && (1ull << id_bits) < n) id_bits++;
+    if (nb_bits > id_bits) nb_bits = id_bits;
+    const uint64_t NB = (1ull << nb_bits) + 1; /* + the sentinel bucket */
+    const int shift = 32 + id_bits - nb_bits;
+    int nt = oracle_num_threads();
+    if (nt < 1) nt = 1;
+    uint64_t *hist = (uint64_t *)calloc((size_t)nt * NB, sizeof(uint64_t));
+    uint64_t *start = (uint64_t *)malloc((NB + 1) * sizeof(uint64_t));
+    uint64_t *uniq = (uint64_t *)calloc(NB + 1, sizeof(uint64_t));
+    if (!hist || !start || !uniq) { free(hist); free(start); free(uniq); return -1; }
+#define BUCKET(key) ((key) == ~0ull ? NB - 1 : (uint64_t)((key) >> shift))
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num();
+        const uint64_t a = nedges * (uint64_t)t / (uint64_t)nt, b = nedges * (uint64_t)(t + 1) / (uint64_t)nt;
+        uint64_t *h = hist + (size_t)t * NB;
+        for (uint64_t k = a; k < b; k++) h[BUCKET(keys[k])]++;
+    }
+    uint64_t acc = 0;
+    for (uint64_t bkt = 0; bkt < NB; bkt++) {
+        start[bkt] = acc;
+        for (int t = 0; t < nt; t++) { const uint64_t c = hist[(size_t)t * NB + bkt]; hist[(size_t)t * NB + bkt] = acc; acc += c; }
+    }
+    start[NB] = acc;
+#pragma omp parallel num_threads(nt)
+    {
+        const int t = omp_get_thread_num();
+        const uint64_t a = nedges * (uint64_t)t / (uint64_t)nt, b = nedges * (uint64_t)(t + 1) / (uint64_t)nt;
+        uint64_t *h = hist + (size_t)t * NB;
+        for (uint64_t k = a; k < b; k++) tmp[h[BUCKET(keys[k])]++] = keys[k];
+    }
+#undef BUCKET
+    /* sort + dedupe every real bucket in place (the sentinel bucket is dropped) */
+    const uint64_t NBR = NB - 1; /* real buckets */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (uint64_t bkt = 0; bkt < NBR; bkt++) {
+        uint64_t *p = tmp + start[bkt];
+        const uint64_t c = start[bkt + 1] - start[bkt];
+        if (!c) continue;
+        qsort(p, c, sizeof(uint64_t), cmp_u64);
+        uint64_t o = 1;
+        for (uint64_t k = 1; k < c; k++)
+            if (p[k] != p[k - 1]) p[o++] = p[k];
+        uniq[bkt + 1] = o;
+    }
+    for (uint64_t bkt = 0; bkt + 1 < NB; bkt++) uniq[bkt + 1] += uniq[bkt];
+    const uint64_t m = uniq[NB - 1];
+    memset(rowptr, 0, (n + 1) * sizeof(uint64_t));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (uint64_t bkt = 0; bkt < NBR; bkt++) {
+        const uint64_t *p = tmp + start[bkt];
+        const uint64_t c = uniq[bkt + 1] - uniq[bkt], o = uniq[bkt];
+        for (uint64_t k = 0; k < c; k++) {
+            colidx[o + k] = (uint32_t)p[k];
+            __atomic_fetch_add(&rowptr[(p[k] >> 32) + 1], 1, __ATOMIC_RELAXED); /* a row may span two buckets */
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) rowptr[i + 1] += rowptr[i];
+    free(hist); free(start); free(uniq);
+    *m_out = m;
+    return (int64_t)n;
 }

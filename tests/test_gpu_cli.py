@@ -66,3 +66,77 @@ def test_unknown_source_vertex_fails_like_the_reference(tmp_path):
     r = subprocess.run([os.path.join(EXE, "bfs"), "--input-dir", str(d), "--output-file", str(tmp_path / "o"),
                         "--directed", "true", "--source-vertex", "12345"], capture_output=True, text=True)
     assert r.returncode != 0 and "Source vertex not found in mapping" in r.stdout   # bfs.cpp:99-102
+
+
+# ------------------------------------------------------------------ gx_graph_load (loader row of the scope table)
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("name", ["example-directed", "example-undirected", "test-wcc-directed", "test-sssp-undirected"])
+def test_gx_graph_load_against_goldens(tmp_path, name, binary):
+    """gx_graph_load (.mtx/.vtx and .grb/.vtb -> device CSR in one call) replaces ReadMatrixMarket + ReadMapping
+    (graphio.cpp:4-60): the loaded graph must give the golden answers of every algorithm that has one."""
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    capi.init(0)
+    for alg in ("BFS", "PR", "WCC", "CDLP", "LCC", "SSSP"):
+        if not os.path.exists(os.path.join(GOLDEN, f"{name}-{alg}")):
+            continue
+        weighted = alg == "SSSP"
+        d, params = prepare(tmp_path / alg, name, weighted, binary)
+        g = capi.Graph.load(str(d), binary, params["directed"])
+        try:
+            ids, ref = golden(name, alg)
+            assert np.array_equal(g.mapping, ids), "graph.vtx / graph.vtb order"
+            dense = {int(v): i for i, v in enumerate(g.mapping)}
+            if alg == "BFS":
+                out = g.bfs(dense[params["bfs_source"]])
+            elif alg == "PR":
+                out = g.pagerank(params["pr_damping"], params["pr_iters"])
+            elif alg == "WCC":
+                out = g.mapping[g.wcc().astype(np.int64)]
+            elif alg == "CDLP":
+                out = g.mapping[g.cdlp(params["cdlp_iters"]).astype(np.int64)]
+            elif alg == "LCC":
+                out = g.lcc()
+            else:
+                assert g.weighted
+                out = g.sssp(dense[params["sssp_source"]])
+            assert validator.validate(alg, out, ref), alg
+        finally:
+            g.free()
+
+
+def test_grb_and_mtx_loaders_agree_on_dirty_input(tmp_path):
+    """A .mtx with self-loops and duplicate entries and the .grb the converter writes from it load as the same
+    graph (both loaders drop self-loops, sort the rows and merge duplicates keeping the smallest weight)."""
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    capi.init(0)
+    d = tmp_path / "dirty"
+    d.mkdir()
+    edges = [(1, 2, 0.5), (1, 2, 0.25), (2, 2, 9.0), (3, 1, 1.5), (2, 3, 0.75), (4, 4, 1.0), (3, 1, 2.5)]
+    with open(d / "graph.mtx", "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n%%GraphBLAS GrB_FP64\n4 4 %d\n" % len(edges))
+        for s, t, w in edges:
+            f.write(f"{s} {t} {w}\n")
+    with open(d / "graph.vtx", "w") as f:
+        f.write("10\n20\n30\n40\n")
+    subprocess.check_call([os.path.join(EXE, "converter"), "--data-dir", str(d), "--weighted", "true", "--directed", "true"])
+    a = capi.Graph.load(str(d), False, True)
+    b = capi.Graph.load(str(d), True, True)
+    try:
+        ra, rb = a.download(), b.download()
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+        assert ra[0].tolist() == [0, 1, 2, 3, 3] and ra[1].tolist() == [1, 2, 0] and ra[2].tolist() == [0.25, 0.75, 1.5]
+        assert np.array_equal(a.mapping, [10, 20, 30, 40]) and np.array_equal(b.mapping, a.mapping)
+    finally:
+        a.free(); b.free()
+    # the same entries as a raw .grb dump (jumbled rows, duplicates and self-loops left in, as GxB could hand them out)
+    hg = graphio.HostGraph(4, np.array([0, 2, 4, 6, 7], dtype=np.uint64), np.array([1, 1, 2, 1, 0, 0, 3], dtype=np.uint32),
+                           np.array([0.5, 0.25, 0.75, 9.0, 1.5, 2.5, 1.0]), True, np.array([10, 20, 30, 40], dtype=np.uint64))
+    d2 = tmp_path / "dirty_grb"
+    graphio.write_graph_dir(str(d2), hg, binary=True)
+    c = capi.Graph.load(str(d2), True, True)
+    try:
+        rc = c.download()
+        assert rc[0].tolist() == [0, 1, 2, 3, 3] and rc[1].tolist() == [1, 2, 0] and rc[2].tolist() == [0.25, 0.75, 1.5]
+    finally:
+        c.free()

@@ -3,6 +3,8 @@ oracle on the same inputs.  Bars (BASELINE.json north_star): BFS levels, WCC
 and CDLP labels bit-exact; PageRank <= 1e-6 relative; LCC <= 1e-9 relative
 (integer ratio, one rounding); SSSP bit-exact (unique fix-point, see
 algo_sssp.cu) -- all far inside the Graphalytics validator's 1e-4."""
+import os
+
 import numpy as np
 import pytest
 
@@ -32,8 +34,19 @@ def check_all(capi, hg, iters_pr=10, iters_cdlp=10, src=None, what="bfs pr wcc c
         src = rmat.max_out_degree_vertex(hg)
     T = oracle.transpose(n, rp, ci) if hg.directed else None
     try:
+        # a directed graph without the cached transposed adjacency takes the push-only BFS and the out-entries-only
+        # WCC (the state the drop-in binaries run in); after gx_graph_cache(GX_CACHE_AT) both take the paths that
+        # use the in-edges -- all four must give the oracle's answer
         if "bfs" in what:
-            assert np.array_equal(g.bfs(src), oracle.bfs(n, rp, ci, src)), "bfs"
+            ref_bfs = oracle.bfs(n, rp, ci, src)
+            assert np.array_equal(g.bfs(src), ref_bfs), "bfs"
+        if "wcc" in what and hg.directed:
+            ref_wcc = oracle.wcc(n, rp, ci, hg.directed, transposed=T)
+            assert np.array_equal(g.wcc(), ref_wcc), "wcc (out-entries only)"
+        if hg.directed:
+            g.cache(capi.GX_CACHE_AT)
+            if "bfs" in what:
+                assert np.array_equal(g.bfs(src), ref_bfs), "bfs (push/pull)"
         if "pr" in what:
             out = g.pagerank(0.85, iters_pr)
             ref = oracle.pagerank(n, rp, ci, 0.85, iters_pr, transposed=T)
@@ -275,10 +288,19 @@ def test_pipelined_upload_with_transposition(capi, monkeypatch):
     bad[-5] = n + 7
     with pytest.raises(capi.GxError):
         capi.Graph.from_csr(n, rp, bad, None, True, cache=capi.GX_CACHE_AT)
+    # column ids beyond 2^bits_for(n): the chunk sort looks at the low bits only, so the runs are not sorted in the
+    # full key -- the merge pass must not run on them (it used to write out of bounds and kill the context)
+    for pos, val in ((7, 0xFFFFFFF0), (ci.size // 2, (1 << 20) + 3), (ci.size - 1, 1 << 31)):
+        bad = ci.copy()
+        bad[pos] = val
+        with pytest.raises(capi.GxError):
+            capi.Graph.from_csr(n, rp, bad, None, True, cache=capi.GX_CACHE_AT)
     rp_bad = rp.copy()
     rp_bad[n // 2] = rp_bad[n // 2 + 1] + 3
     with pytest.raises(capi.GxError):
         capi.Graph.from_csr(n, rp_bad, ci, None, True, cache=capi.GX_CACHE_AT)
+    # ... and the context is still alive afterwards
+    check(capi.Graph.from_csr(n, rp, ci, w, True, cache=capi.GX_CACHE_AT))
 
 
 def test_lcc_every_apex_size_class(capi):
@@ -463,8 +485,9 @@ def test_rmat24_undirected_against_oracle(capi):
 
 def test_rmat22_undirected_lcc(capi):
     """BASELINE config [3]: LCC on the undirected RMAT-22 graph (membership tables, owner-ordered entries).
-    The oracle's cost is quadratic in hub degrees, so a random sample of vertices is compared (<= 1e-9 relative);
-    every value must lie in [0, 1] and vertices of degree < 2 must be 0."""
+    A random sample of vertices AND the 32 largest hubs are compared with the oracle (<= 1e-9 relative) -- the hubs are
+    where the membership tables and the owner-ordered runs do their work (the oracle walks a hub's neighbours on all
+    host threads: seconds per hub); every value must lie in [0, 1] and vertices of degree < 2 must be 0."""
     g = capi.Graph.rmat(22, False, want_mapping=False)
     try:
         rp, ci, _ = g.download()
@@ -473,11 +496,13 @@ def test_rmat22_undirected_lcc(capi):
         deg = np.diff(rp.astype(np.int64))
         assert ((out >= 0.0) & (out <= 1.0)).all() and (out[deg < 2] == 0.0).all()
         rng = np.random.default_rng(3)
-        cand = rng.integers(0, n, 20000)
-        sample = np.unique(cand[deg[cand] < 2000])[:4000].astype(np.uint64)   # hubs would take minutes on the host
+        hubs = np.argsort(deg)[-32:]
+        sample = np.unique(np.concatenate([rng.integers(0, n, 4000), hubs])).astype(np.uint64)
+        oracle.set_threads(os.cpu_count() or 1)
         ref = oracle.lcc(n, rp, ci, False, subset=sample)
         idx = sample.astype(np.int64)
         assert rel_err(out[idx], ref[idx]) <= LCC_TOL
+        assert rel_err(out[hubs], ref[hubs]) <= LCC_TOL and (out[hubs] > 0).all(), "hubs"
         assert (out[idx] > 0).sum() > 100, "the sample must exercise non-trivial values"
     finally:
         g.free()
