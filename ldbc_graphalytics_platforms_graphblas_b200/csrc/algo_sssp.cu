@@ -27,6 +27,7 @@
 // every bit of the result, is the same.  Several GPUs still run plain sweeps.
 // Algorithmic bytes (one-pass bound): 12m + 8(n+1) + 16n.
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -55,11 +56,30 @@ __global__ void k_sssp_init(unsigned long long *__restrict__ dist, uint64_t n, u
 // (k_sssp_compact): appending winners to a queue from here funnels millions of atomics per round
 // through one counter.  state == NULL (multi-GPU): the next frontier is derived from the
 // min-reduced distances instead.
+//
+// Several GPUs with delta-stepping (P != NULL): every rank holds a full-length distance array, mapped into all
+// peers.  A rank's copy is AUTHORITATIVE for the vertices of its row block and a filter (a stale upper bound)
+// for all others: an improvement that passes the local atomicMin is forwarded to the owner's copy by a
+// system-scope atomicMin over NVLink -- no all-reduce of the distances, only improvements travel.
+struct SsspPeers {
+    unsigned long long *dist[MAX_PEERS]; // rank r's distance array as seen from here
+    uint64_t bound[MAX_PEERS + 1];       // row-block boundaries
+    int nranks, rank;
+};
+
 __device__ __forceinline__ bool sssp_relax_edge(unsigned long long *dist, uint32_t *state, uint32_t v, double nd,
-                                                unsigned long long thresh)
+                                                unsigned long long thresh, const SsspPeers *__restrict__ P = nullptr)
 {
     const unsigned long long nb = (unsigned long long)__double_as_longlong(nd);
     if (nb >= dist[v]) return false;
+    if (P) {
+        const unsigned long long was = atomicMin_system(&dist[v], nb);
+        if (nb >= was) return false;
+        int o = 0;
+        while (o + 1 < P->nranks && v >= P->bound[o + 1]) o++;
+        if (o != P->rank) atomicMin_system(&P->dist[o][v], nb);
+        return false;
+    }
     const unsigned long long old = atomicMin(&dist[v], nb);
     if (nb >= old || state == nullptr) return false;
     if (nb < thresh) { if (state[v] != 1u) state[v] = 1u; return true; }
@@ -83,9 +103,12 @@ __device__ __forceinline__ double ld_adj_f64(const double *p)
 
 // Relax entries e0, e0 + step, ... (up to 4, below `hi`): the 4 entry loads and then the 4 distance
 // loads are in flight together; only actual improvements go on to the atomic.
+// Entries with a weight <= min_w are skipped (the heavy phase walks whole rows of the graph's own adjacency and
+// leaves out the light entries; min_w < 0 relaxes everything).
 __device__ __forceinline__ unsigned sssp_relax4(const uint32_t *__restrict__ col, const double *__restrict__ w, uint64_t e0,
                                                 uint64_t step, uint64_t hi, double du, unsigned long long *dist,
-                                                uint32_t *state, unsigned long long thresh)
+                                                uint32_t *state, unsigned long long thresh, double min_w,
+                                                const SsspPeers *__restrict__ P = nullptr)
 {
     uint32_t v[4];
     double nd[4];
@@ -95,8 +118,10 @@ __device__ __forceinline__ unsigned sssp_relax4(const uint32_t *__restrict__ col
     for (int j = 0; j < 4; j++) {
         const uint64_t e = e0 + (uint64_t)j * step;
         ok[j] = e < hi;
+        const double we = ok[j] ? ld_adj_f64(w + e) : 0.0;
+        ok[j] = ok[j] && we > min_w;
         v[j] = ok[j] ? ld_adj(col + e) : 0u;
-        nd[j] = ok[j] ? du + ld_adj_f64(w + e) : 0.0;
+        nd[j] = du + we;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) dv[j] = ok[j] ? dist[v[j]] : 0ull;
@@ -105,7 +130,7 @@ __device__ __forceinline__ unsigned sssp_relax4(const uint32_t *__restrict__ col
     for (int j = 0; j < 4; j++) {
         if (!ok[j]) continue;
         cntd++;
-        if ((unsigned long long)__double_as_longlong(nd[j]) < dv[j]) sssp_relax_edge(dist, state, v[j], nd[j], thresh);
+        if ((unsigned long long)__double_as_longlong(nd[j]) < dv[j]) sssp_relax_edge(dist, state, v[j], nd[j], thresh, P);
     }
     return cntd;
 }
@@ -219,37 +244,45 @@ k_sssp_compact(const uint32_t *__restrict__ state, uint64_t n, uint32_t *__restr
 }
 
 // ---- delta-stepping on one GPU: light / heavy entries -----------------------------------------
+// The light entries (w <= delta: ~10 % of them at the default bucket width) are compacted into an adjacency of
+// their own, row by row; the heavy phase walks the graph's own rows and skips the light ones.  Building this reads
+// the weights twice and the column ids of the light entries once (~27 bytes per entry), against a full partitioned
+// copy of every row (12 bytes written per entry plus row ids: 4x the traffic and 10x the allocation) before.
 struct SsspCache {
     double delta = 0.0;
-    DevBuf<uint32_t> col;     // m: every row's light entries (w <= delta) first, then the heavy ones
-    DevBuf<double> w;         // m
-    DevBuf<uint32_t> nlight;  // n: light entries of the row
+    uint64_t ml = 0;          // light entries
+    DevBuf<uint64_t> lrowptr; // n+1
+    DevBuf<uint32_t> lcol;    // ml
+    DevBuf<double> lw;        // ml
 };
 
-// flag[e] = 1 for a light entry; one extra item (0) so that the exclusive scan ends with the total
-__global__ void k_sssp_light_flags(const double *__restrict__ w, uint64_t m, double delta, uint32_t *__restrict__ flag)
+struct LightFlag {
+    double delta;
+    __host__ __device__ __forceinline__ uint32_t operator()(const double &x) const { return x <= delta ? 1u : 0u; }
+};
+
+// lrowptr[v] = light entries before row v among the entries [e0, e1) (rows [v0, v1]: the whole graph on one GPU,
+// the rank's row block on several); L = exclusive prefix count of light entries over that entry range
+__global__ void k_sssp_lrowptr(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ L, const double *__restrict__ w,
+                               uint64_t v0, uint64_t v1, uint64_t e0, uint64_t e1, double delta, uint64_t *__restrict__ lrowptr)
 {
-    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; e <= m; e += stride) flag[e] = (e < m && ld_stream_f64(w + e) <= delta) ? 1u : 0u;
+    const uint64_t total = (uint64_t)L[e1 - e0 - 1] + (w[e1 - 1] <= delta ? 1u : 0u);
+    for (; v <= v1; v += stride) {
+        const uint64_t e = rowptr[v];
+        lrowptr[v] = e < e1 ? (uint64_t)L[e - e0] : total;
+    }
 }
 
-// stable partition of every row into light | heavy: L = exclusive prefix count of light entries
-__global__ void k_sssp_partition(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ row_of, const uint32_t *__restrict__ col,
-                                 const double *__restrict__ w, const uint32_t *__restrict__ L, uint64_t m, double delta,
-                                 uint32_t *__restrict__ col_p, double *__restrict__ w_p, uint32_t *__restrict__ nlight)
+__global__ void k_sssp_compact_light(const uint32_t *__restrict__ col, const double *__restrict__ w, const uint32_t *__restrict__ L,
+                                     uint64_t e0, uint64_t e1, double delta, uint32_t *__restrict__ lcol, double *__restrict__ lw)
 {
-    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t e = e0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; e < m; e += stride) {
-        const uint32_t r = row_of[e];
-        const uint64_t a = rowptr[r], b = rowptr[r + 1];
-        const uint32_t la = L[a], nl = L[b] - la, lr = L[e] - la;
+    for (; e < e1; e += stride) {
         const double we = ld_stream_f64(w + e);
-        const uint64_t dst = we <= delta ? a + lr : a + nl + ((e - a) - lr);
-        col_p[dst] = ld_stream(col + e);
-        w_p[dst] = we;
-        if (e == a) nlight[r] = nl;
+        if (we <= delta) { const uint32_t d = L[e - e0]; lcol[d] = col[e]; lw[d] = we; }
     }
 }
 
@@ -257,13 +290,14 @@ __global__ void k_sssp_partition(const uint64_t *__restrict__ rowptr, const uint
 // entries are re-queued as CHUNK pieces for whole CTAs (k_sssp_relax_pieces).  Light expansion stamps
 // the vertex with the current epoch: the stamped vertices are the bucket's members whose heavy
 // entries are still due.
+// (rowptr, col, w): the light adjacency for the light rounds, the graph's own for the heavy phase (min_w = delta)
 template <int G, bool HEAVY>
 __global__ void __launch_bounds__(256)
-k_sssp_expand(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ nlight, const uint32_t *__restrict__ col,
+k_sssp_expand(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
               const double *__restrict__ w, const uint32_t *__restrict__ queue, const unsigned long long *__restrict__ qn_p,
               unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, uint32_t *__restrict__ stamp, uint32_t epoch,
               uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, uint64_t *__restrict__ big_end,
-              SsspCounters *__restrict__ cnt, unsigned long long thresh)
+              SsspCounters *__restrict__ cnt, unsigned long long thresh, double min_w, const SsspPeers *__restrict__ P)
 {
     const unsigned sub = threadIdx.x & (G - 1);
     uint64_t gi = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -272,9 +306,8 @@ k_sssp_expand(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ 
     unsigned long long relaxed = 0;
     for (; gi < qn; gi += ng) {
         const uint32_t u = queue[gi];
-        const uint64_t a = rowptr[u], b = rowptr[u + 1], mid = a + nlight[u];
-        const uint64_t lo = HEAVY ? mid : a, hi = HEAVY ? b : mid;
-        if (!HEAVY && sub == 0) stamp[u] = epoch;
+        const uint64_t lo = rowptr[u], hi = rowptr[u + 1];
+        if (!HEAVY && stamp && sub == 0) stamp[u] = epoch;
         if (hi - lo > 32u * G) { // more than 32 trips of the group: whole CTAs take it over
             const uint64_t nch = (hi - lo + CHUNK - 1) / CHUNK;
             const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << ((lane_id() / G) * G)); // groups diverge here
@@ -285,7 +318,7 @@ k_sssp_expand(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ 
             continue;
         }
         const double du = __longlong_as_double((long long)dist[u]);
-        for (uint64_t e = lo + sub; e < hi; e += 4 * G) relaxed += sssp_relax4(col, w, e, G, hi, du, dist, state, thresh);
+        for (uint64_t e = lo + sub; e < hi; e += 4 * G) relaxed += sssp_relax4(col, w, e, G, hi, du, dist, state, thresh, min_w, P);
     }
     relaxed = warp_sum(relaxed);
     if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
@@ -295,7 +328,7 @@ __global__ void __launch_bounds__(256)
 k_sssp_relax_pieces(const uint32_t *__restrict__ col, const double *__restrict__ w, const uint32_t *__restrict__ big_row,
                     const uint64_t *__restrict__ big_begin, const uint64_t *__restrict__ big_end,
                     unsigned long long *__restrict__ dist, uint32_t *__restrict__ state, SsspCounters *__restrict__ cnt,
-                    unsigned long long thresh)
+                    unsigned long long thresh, double min_w, const SsspPeers *__restrict__ P)
 {
     const unsigned long long nbig = cnt->big_count;
     unsigned long long relaxed = 0;
@@ -303,7 +336,7 @@ k_sssp_relax_pieces(const uint32_t *__restrict__ col, const double *__restrict__
         const uint64_t b0 = big_begin[c], end = big_end[c];
         const uint64_t e_end = (b0 + CHUNK < end) ? b0 + CHUNK : end;
         const double du = __longlong_as_double((long long)dist[big_row[c]]);
-        for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 4 * 256) relaxed += sssp_relax4(col, w, e, 256, e_end, du, dist, state, thresh);
+        for (uint64_t e = b0 + threadIdx.x; e < e_end; e += 4 * 256) relaxed += sssp_relax4(col, w, e, 256, e_end, du, dist, state, thresh, min_w, P);
     }
     relaxed = warp_sum(relaxed);
     if (lane_id() == 0 && relaxed) atomicAdd(&cnt->relaxed, relaxed);
@@ -431,28 +464,36 @@ namespace gx {
 
 static SsspCache *build_sssp_cache(gx_graph *g, double delta)
 {
-    const uint64_t n = g->n, m = g->m;
-    GX_REQUIRE(m < 0xFFFFFFFFull, "SSSP light/heavy partition needs nnz < 2^32");
+    const uint64_t n = g->n;
     SsspCache *sc = new SsspCache();
     sc->delta = delta;
-    sc->col.alloc(m ? m : 1);
-    sc->w.alloc(m ? m : 1);
-    sc->nlight.alloc(n);
-    sc->nlight.zero();
-    if (!m) return sc;
-    DevBuf<uint32_t> L(m + 1), rows(m);
+    sc->lrowptr.alloc(n + 1);
+    // several GPUs: a rank expands the rows of its block only, so only their light entries are compacted
+    const Partition &part = g->out.plan.part;
+    const uint64_t v0 = multi() ? part.lo : 0, v1 = multi() ? part.hi : n;
+    uint64_t ends[2] = {0, g->m};
+    if (multi()) {
+        read_back(&ends[0], g->out.rowptr.p + v0, sizeof(uint64_t));
+        read_back(&ends[1], g->out.rowptr.p + v1, sizeof(uint64_t));
+    }
+    const uint64_t e0 = ends[0], e1 = ends[1], cnt = e1 - e0;
+    GX_REQUIRE(cnt < 0xFFFFFFFFull, "SSSP light/heavy split needs fewer than 2^32 entries per rank");
+    if (!cnt) { sc->lrowptr.zero(); sc->lcol.alloc(1); sc->lw.alloc(1); return sc; }
+    DevBuf<uint32_t> L(cnt);
     {
-        // L[e] = light entries before e; L[m] = their total
-        GX_LAUNCH(k_sssp_light_flags, grid_persistent(8), 256, 0, g->out.w.p, m, delta, L.p);
+        // L[e] = light entries before e: the flags are computed on the fly from the weights (no flag array)
+        auto flags = thrust::make_transform_iterator((const double *)g->out.w.p + e0, LightFlag{delta});
         size_t tb = 0;
-        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, L.p, L.p, (int64_t)(m + 1), ctx().stream));
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, L.p, (int64_t)cnt, ctx().stream));
         DevBuf<char> tmp(tb);
-        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, L.p, L.p, (int64_t)(m + 1), ctx().stream));
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags, L.p, (int64_t)cnt, ctx().stream));
         count_launch();
     }
-    expand_row_ids(g->out.rowptr.p, n, m, rows.p);
-    GX_LAUNCH(k_sssp_partition, grid_persistent(8), 256, 0, g->out.rowptr.p, rows.p, g->out.col.p, g->out.w.p, L.p, m, delta,
-              sc->col.p, sc->w.p, sc->nlight.p);
+    GX_LAUNCH(k_sssp_lrowptr, grid_persistent(8), 256, 0, g->out.rowptr.p, L.p, g->out.w.p, v0, v1, e0, e1, delta, sc->lrowptr.p);
+    read_back(&sc->ml, sc->lrowptr.p + v1, sizeof(uint64_t));
+    sc->lcol.alloc(sc->ml ? sc->ml : 1);
+    sc->lw.alloc(sc->ml ? sc->ml : 1);
+    GX_LAUNCH(k_sssp_compact_light, grid_persistent(8), 256, 0, g->out.col.p, g->out.w.p, L.p, e0, e1, delta, sc->lcol.p, sc->lw.p);
     return sc;
 }
 
@@ -486,10 +527,10 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
             GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, state.p);
             // (grid capped: every warp ends with one atomic on the shared counters)
             const unsigned g_light = grid_for(qn * 8, 256) < grid_persistent(8) ? grid_for(qn * 8, 256) : grid_persistent(8);
-            GX_LAUNCH((k_sssp_expand<8, false>), g_light, 256, 0, rp, sc.nlight.p, sc.col.p, sc.w.p, queue, qn_dev.p,
-                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T));
-            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.col.p, sc.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
-                      state.p, cnt.p, bits(T));
+            GX_LAUNCH((k_sssp_expand<8, false>), g_light, 256, 0, sc.lrowptr.p, sc.lcol.p, sc.lw.p, queue, qn_dev.p,
+                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), -1.0, nullptr);
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.lcol.p, sc.lw.p, big_row.p, big_begin.p, big_end.p, dist.p,
+                      state.p, cnt.p, bits(T), -1.0, nullptr);
             GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, state.p, 1u, n, next_q, &cnt.p->next_count);
             SsspCounters h;
             read_back(&h, cnt.p, sizeof(h)); // also orders the host-side qn against its async copy
@@ -503,10 +544,10 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
         if (expanded) {
             cnt.zero();
             GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, stamp.p, epoch, n, next_q, &cnt.p->r_count);
-            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, rp, sc.nlight.p, sc.col.p, sc.w.p, next_q, &cnt.p->r_count,
-                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T));
-            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.col.p, sc.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
-                      state.p, cnt.p, bits(T));
+            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, rp, g->out.col.p, g->out.w.p, next_q, &cnt.p->r_count,
+                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, nullptr);
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, g->out.col.p, g->out.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
+                      state.p, cnt.p, bits(T), delta, nullptr);
             // a heavy entry adds more than delta to a distance >= T - delta, so nothing lands below T;
             // should rounding ever say otherwise, the vertex is in state 1 and the bucket simply goes on
             GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, state.p, 1u, n, queue, &cnt.p->next_count);
@@ -536,6 +577,154 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
         if (!qn) break;
     }
     GX_LAUNCH(k_sssp_out, grid_persistent(8), 256, 0, dist.p, n, g->res_f64.p);
+}
+
+// ---- several GPUs: delta-stepping, owner-computes, improvements forwarded by peer atomics ---------------------
+// Per owned vertex two marks: the distance at which it was last light- / heavy-expanded.  A vertex is due for
+// the light rounds of the bucket below T when its distance is < T and < its light mark; for the heavy phase that
+// closes the bucket when its distance is < T and < its heavy mark.  The scan that builds a round's queue also
+// returns the smallest distance >= T that is still waiting, so empty buckets are skipped.
+struct SsspRound { unsigned long long qn, neg_far_min, relaxed; }; // the first two are max-reduced over the ranks
+
+__global__ void k_sssp_m_init(unsigned long long *__restrict__ dist, uint64_t n, uint32_t src, unsigned long long *__restrict__ ldone,
+                              unsigned long long *__restrict__ hdone, uint64_t own)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) {
+        dist[v] = (v == src) ? 0ull : INF_BITS;
+        if (v < own) { ldone[v] = INF_BITS; hdone[v] = INF_BITS; }
+    }
+}
+
+template <bool HEAVY>
+__global__ void __launch_bounds__(256)
+k_sssp_m_build(const unsigned long long *__restrict__ dist, unsigned long long *__restrict__ done, uint64_t v0, uint64_t v1,
+               unsigned long long thresh, uint32_t *__restrict__ queue, SsspCounters *__restrict__ cnt)
+{
+    const uint64_t own = v1 - v0, nround = (own + 1023) & ~1023ull;
+    unsigned long long fmin = ~0ull;
+    for (uint64_t base = (uint64_t)blockIdx.x * 1024; base < nround; base += (uint64_t)gridDim.x * 1024) {
+        const uint64_t i4 = base + 4ull * threadIdx.x;
+        unsigned take = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t i = i4 + j;
+            if (i < own) {
+                const unsigned long long d = dist[v0 + i];
+                if (d < done[i]) {
+                    if (d < thresh) { take |= 1u << j; done[i] = d; }
+                    else if (!HEAVY) fmin = d < fmin ? d : fmin;
+                }
+            }
+        }
+        block_compact4(take, v0 + i4, queue, &cnt->next_count);
+    }
+    if (!HEAVY) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, fmin, o); fmin = x < fmin ? x : fmin; }
+        if (lane_id() == 0 && fmin != ~0ull) atomicMin(&cnt->far_min, fmin);
+    }
+}
+
+__global__ void k_sssp_m_pack(const SsspCounters *__restrict__ cnt, SsspRound *__restrict__ r)
+{
+    r->qn = cnt->next_count;
+    r->neg_far_min = ~cnt->far_min;
+    r->relaxed = cnt->relaxed;
+}
+
+__global__ void k_sssp_m_out(const unsigned long long *__restrict__ dist, uint64_t v0, uint64_t v1, double *__restrict__ out)
+{
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < v1; v += stride) out[v] = __longlong_as_double((long long)dist[v]);
+}
+
+// returns false when the peer mapping is unavailable (the caller then runs the replicated sweeps)
+static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uint64_t &relaxed, uint32_t &rounds)
+{
+    Context &c = ctx();
+    const uint64_t n = g->n, m = g->m;
+    const double delta = sc.delta;
+    const Partition &part = g->out.plan.part;
+    const uint64_t v0 = part.lo, v1 = part.hi, own = v1 - v0;
+    PeerBuf db;
+    peer_alloc(db, n * sizeof(unsigned long long));
+    if (!db.shared) { peer_free(db); return false; }
+    struct Release { PeerBuf &b; ~Release() { peer_free(b); } } release{db};
+    unsigned long long *dist = (unsigned long long *)db.local;
+    DevBuf<unsigned long long> ldone(own ? own : 1), hdone(own ? own : 1);
+    DevBuf<uint32_t> queue(own + 1024);
+    const uint64_t big_cap = m / CHUNK + m / 256 + 16;
+    DevBuf<uint32_t> big_row(big_cap);
+    DevBuf<uint64_t> big_begin(big_cap), big_end(big_cap);
+    DevBuf<SsspCounters> cnt(1);
+    DevBuf<SsspRound> round(1);
+    DevBuf<SsspPeers> peers(1);
+    {
+        SsspPeers h{};
+        h.nranks = c.nranks;
+        h.rank = c.rank;
+        for (int r = 0; r < c.nranks; r++) { h.dist[r] = (unsigned long long *)db.peer[r]; h.bound[r] = part.b[r]; }
+        h.bound[c.nranks] = part.b[c.nranks];
+        GX_CUDA(cudaMemcpyAsync(peers.p, &h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
+        GX_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    auto bits = [](double x) { unsigned long long b; memcpy(&b, &x, sizeof(b)); return b; };
+    GX_LAUNCH(k_sssp_m_init, grid_persistent(8), 256, 0, dist, n, (uint32_t)src, ldone.p, hdone.p, own);
+    round.zero();
+    allreduce(round.p, 2, Dt::U64, Red::Max); // nobody may forward into a rank's array before that rank has initialised it
+    double T = delta;
+    bool expanded = false; // some rank light-expanded a vertex since the last heavy phase
+    // one round: build the queue of due vertices, expand them, exchange {queue size, smallest waiting distance};
+    // the all-reduce is also the barrier after which every forwarded improvement of the round has landed
+    auto run_round = [&](bool heavy, SsspRound &h) {
+        cnt.zero();
+        GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
+        if (heavy) {
+            GX_LAUNCH(k_sssp_m_build<true>, grid_persistent(8), 256, 0, dist, hdone.p, v0, v1, bits(T), queue.p, cnt.p);
+            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue.p,
+                      &cnt.p->next_count, dist, nullptr, nullptr, 0u, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, peers.p);
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, g->out.col.p, g->out.w.p, big_row.p, big_begin.p, big_end.p, dist,
+                      nullptr, cnt.p, bits(T), delta, peers.p);
+        } else {
+            GX_LAUNCH(k_sssp_m_build<false>, grid_persistent(8), 256, 0, dist, ldone.p, v0, v1, bits(T), queue.p, cnt.p);
+            GX_LAUNCH((k_sssp_expand<8, false>), grid_persistent(8), 256, 0, sc.lrowptr.p, sc.lcol.p, sc.lw.p, queue.p, &cnt.p->next_count,
+                      dist, nullptr, nullptr, 0u, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), -1.0, peers.p);
+            GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.lcol.p, sc.lw.p, big_row.p, big_begin.p, big_end.p, dist, nullptr,
+                      cnt.p, bits(T), -1.0, peers.p);
+        }
+        GX_LAUNCH(k_sssp_m_pack, 1, 1, 0, cnt.p, round.p);
+        allreduce(round.p, 2, Dt::U64, Red::Max);
+        read_back(&h, round.p, sizeof(h));
+        relaxed += h.relaxed;
+        rounds++;
+    };
+    for (;;) {
+        SsspRound h;
+        for (;;) { // light rounds until no rank has a due vertex below T
+            run_round(false, h);
+            if (!h.qn) break;
+            expanded = true;
+        }
+        if (expanded) { // the bucket is stable: heavy entries of everything in it that moved, once
+            SsspRound hh;
+            run_round(true, hh);
+            expanded = false;
+            continue; // (re-scan: the heavy phase may have created due vertices, and the waiting minimum moved)
+        }
+        const unsigned long long fmin_bits = ~h.neg_far_min;
+        if (fmin_bits == ~0ull) break; // nothing is waiting anywhere
+        double fmin;
+        memcpy(&fmin, &fmin_bits, sizeof(fmin));
+        T += delta;
+        if (fmin >= T) T = fmin + delta; // skip the empty buckets
+    }
+    GX_LAUNCH(k_sssp_m_out, grid_persistent(8), 256, 0, dist, v0, v1, g->res_f64.p);
+    allgatherv(g->res_f64.p, Dt::F64, part);
+    GX_CUDA(cudaStreamSynchronize(c.stream));
+    return true;
 }
 
 } // namespace gx
@@ -573,9 +762,10 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
         double delta = 8.0 * (double)g->mean_weight * (double)n / (double)(m ? m : 1);
         if (const char *e = getenv("GX_SSSP_DELTA")) delta = atof(e); // tuning knob; 0 = plain sweeps
         const char *lh = getenv("GX_SSSP_LH");                        // GX_SSSP_LH=0: near/far without the light/heavy split
-        const bool light_heavy = !multi() && delta > 0.0 && m > 0 && !(lh && lh[0] == '0');
+        const bool light_heavy = delta > 0.0 && m > 0 && !(lh && lh[0] == '0') && (!multi() || c.nranks <= MAX_PEERS);
         uint64_t relaxed = 0;
         uint32_t rounds = 0;
+        bool done = false;
         if (light_heavy) {
             SsspCache *sc = (SsspCache *)g->sssp_cache;
             if (!sc || sc->delta != delta) {
@@ -584,8 +774,10 @@ extern "C" int gx_sssp(gx_graph *g, uint64_t src, double *dist_host)
                 g->sssp_cache = sc = build_sssp_cache(g, delta);
             }
             PhaseTimer tk(&c.timing.kernel_ms);
-            sssp_delta_stepping(g, *sc, src, relaxed, rounds);
-        } else {
+            if (multi()) done = sssp_multi_delta(g, *sc, src, relaxed, rounds);
+            else { sssp_delta_stepping(g, *sc, src, relaxed, rounds); done = true; }
+        }
+        if (!done) {
         DevBuf<unsigned long long> dist(n);
         DevBuf<uint32_t> inq(n), q0(n), q1(n);
         DevBuf<unsigned long long> prev(multi() ? n : 0);

@@ -113,7 +113,7 @@ def test_grb_and_mtx_loaders_agree_on_dirty_input(tmp_path):
     d.mkdir()
     edges = [(1, 2, 0.5), (1, 2, 0.25), (2, 2, 9.0), (3, 1, 1.5), (2, 3, 0.75), (4, 4, 1.0), (3, 1, 2.5)]
     with open(d / "graph.mtx", "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%%GraphBLAS GrB_FP64\n4 4 %d\n" % len(edges))
+        f.write(f"%%MatrixMarket matrix coordinate real general\n%%GraphBLAS GrB_FP64\n4 4 {len(edges)}\n")
         for s, t, w in edges:
             f.write(f"{s} {t} {w}\n")
     with open(d / "graph.vtx", "w") as f:

@@ -81,6 +81,53 @@ while frontier.size:
     frontier = np.nonzero(dist_v < prev)[0]
 assert np.array_equal(dist_v, oracle.sssp(n, g.rowptr, g.colidx, g.weights, src)), "partitioned SSSP"
 
+# SSSP with delta-stepping on several GPUs (algo_sssp.cu sssp_multi_delta): every rank keeps a full-length
+# distance array that is authoritative for its own block and a filter elsewhere; an improvement that passes the
+# local minimum is forwarded to the owner (here: the owner's block takes the minimum over the ranks' copies at the
+# end of a round, the other entries stay local); two marks per owned vertex say at which distance it was last
+# light- / heavy-expanded; {queue size, smallest waiting distance} are max-/min-reduced every round
+delta = 8.0 * g.weights.mean() * n / ci.size
+lo_, hi_ = bo[rank], bo[rank + 1]
+dl = np.full(n, np.inf); dl[src] = 0.0
+ldone = np.full(n, np.inf); hdone = np.full(n, np.inf)
+def exchange():
+    t = torch.from_numpy(dl.copy()); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dl[lo_:hi_] = t.numpy()[lo_:hi_]
+def round_(heavy, T):
+    done = hdone if heavy else ldone
+    own = np.arange(lo_, hi_)
+    due = own[(dl[own] < done[own]) & (dl[own] < T)]
+    wait = own[(dl[own] < done[own]) & (dl[own] >= T)]
+    done[due] = dl[due]
+    for u in due:
+        du = dl[u]
+        for e in range(rp[u], rp[u + 1]):
+            we = g.weights[e]
+            if (we > delta) == heavy:
+                dl[ci[e]] = min(dl[ci[e]], du + we)
+    exchange()
+    q = torch.tensor([float(due.size)]); dist.all_reduce(q, op=dist.ReduceOp.MAX)
+    fm = torch.tensor([dl[wait].min() if (wait.size and not heavy) else np.inf], dtype=torch.float64)
+    dist.all_reduce(fm, op=dist.ReduceOp.MIN)
+    return int(q), float(fm)
+T, expanded = delta, False
+while True:
+    while True:
+        qn, fmin = round_(False, T)
+        if not qn:
+            break
+        expanded = True
+    if expanded:
+        round_(True, T); expanded = False
+        continue
+    if not np.isfinite(fmin):
+        break
+    T += delta
+    if fmin >= T:
+        T = fmin + delta
+got = allgatherv(dl, bo)
+assert np.array_equal(got, oracle.sssp(n, g.rowptr, g.colidx, g.weights, src)), "multi-GPU delta-stepping SSSP"
+
 # Transposition split by column range (graph.cu transpose_partitioned): a rank keeps the (column, row) pairs of
 # its vertex slice in row-major order, sorts them stably by column, and the slices concatenate to A'
 cb = partition.column_slices(n, world)
