@@ -302,22 +302,42 @@ HostMatrix ReadGrbFile(const std::string &path)
         std::vector<double> Ax;
         if (weighted) { Ax.resize(nvals); rd(f, Ax.data(), nvals, path); }
         // same policy as the .mtx path (coo_to_csr): self-loops dropped, rows sorted, duplicates merged
-        // (smallest weight kept), so both loaders give the same graph for the same data
+        // (smallest weight kept), so both loaders give the same graph for the same data.  A dump that is already
+        // clean -- what the converter writes -- is adopted as it is after one parallel check.
         if (!is_hyper && nvec != nrows) throw std::runtime_error("Sparse .grb with nvec != nrows: " + path);
-        std::vector<uint32_t> src(nvals), dst(nvals);
         const unsigned T = loader_threads((size_t)nvec, 1u << 14);
+        std::atomic<int> dirty{0}, out_of_range{0};
         run_parallel(T, [&](unsigned t) {
             for (uint64_t k = nvec * t / T; k < nvec * (t + 1) / T; k++) {
-                const uint32_t row = (uint32_t)(is_hyper ? Ah[k] : k);
+                const uint64_t row = is_hyper ? Ah[k] : k;
                 for (uint64_t e = Ap[k]; e < Ap[k + 1]; e++) {
-                    if (Ai[e] >= nrows) throw std::runtime_error("Column index out of range in " + path);
-                    src[e] = row;
-                    dst[e] = (uint32_t)Ai[e];
+                    if (Ai[e] >= nrows) { out_of_range = 1; return; }
+                    if (Ai[e] == row || (e > Ap[k] && Ai[e] <= Ai[e - 1])) dirty = 1;
                 }
             }
         });
-        { std::vector<GrB_Index>().swap(Ai); std::vector<GrB_Index>().swap(Ap); }
-        A = coo_to_csr(nrows, src, dst, Ax, weighted);
+        if (out_of_range) throw std::runtime_error("Column index out of range in " + path);
+        if (!dirty && !is_hyper) {
+            A.nrows = nrows;
+            A.nvals = nvals;
+            A.iso = !weighted;
+            A.Aj.resize(nvals);
+            run_parallel(T, [&](unsigned t) {
+                for (uint64_t e = nvals * t / T; e < nvals * (t + 1) / T; e++) A.Aj[e] = (uint32_t)Ai[e];
+            });
+            A.Ap = std::move(Ap);
+            A.Ax = std::move(Ax);
+        } else {
+            std::vector<uint32_t> src(nvals), dst(nvals);
+            run_parallel(T, [&](unsigned t) {
+                for (uint64_t k = nvec * t / T; k < nvec * (t + 1) / T; k++) {
+                    const uint32_t row = (uint32_t)(is_hyper ? Ah[k] : k);
+                    for (uint64_t e = Ap[k]; e < Ap[k + 1]; e++) { src[e] = row; dst[e] = (uint32_t)Ai[e]; }
+                }
+            });
+            { std::vector<GrB_Index>().swap(Ai); std::vector<GrB_Index>().swap(Ap); }
+            A = coo_to_csr(nrows, src, dst, Ax, weighted);
+        }
     } catch (...) {
         fclose(f);
         throw;
