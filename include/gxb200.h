@@ -48,6 +48,9 @@ typedef struct gx_graph gx_graph; /* opaque: device-resident CSR (+ cached CSC, 
 int gx_init(int device);
 int gx_finalize(void);
 int gx_device_count(void);
+/* Grows the library's device memory pool to `bytes` ahead of time (capped at 60 % of the free memory; best effort), so
+ * that the algorithms' scratch buffers are not mapped on first use inside a timed window. */
+int gx_reserve(uint64_t bytes);
 const char *gx_last_error(void);
 
 /* Multi-GPU: one process per GPU.  Rank 0 calls gx_comm_unique_id, ships the 128 bytes to the
@@ -144,6 +147,29 @@ const char *gx_profile_report(void);
 /* Pinned host memory for callers that want full-speed uploads. */
 int gx_host_alloc(void **p, uint64_t bytes);
 int gx_host_free(void *p);
+/* Page-lock / release host arrays the caller already owns (the CSR arrays a loader filled); best effort. */
+int gx_host_register(const void *p, uint64_t bytes);
+int gx_host_unregister(const void *p);
+
+/* ---- result files ------------------------------------------------------------------------
+ * Replaces SerializeBFSResult / SerializePageRankResult / SerializeWCCResult / SerializeCDLPResult / SerializeLCCResult /
+ * SerializeSSSPResult (bfs.cpp:11-68, pr.cpp:17-45, wcc.cpp:11-37, cdlp.cpp:21-52, lcc.cpp:17-59, sssp.cpp:11-51): one
+ * line "<ids[i]> <value>" per vertex in array order; INT64 / UINT64 in decimal (UINT64: value_map[values[i]] when
+ * value_map is given -- CDLP prints mapping[label], cdlp.cpp:48), FP64 as precision(16) << scientific with +inf written
+ * as the literal `infinity` (sssp.cpp:41-46).  Formatted on all host threads; host-only, needs no device. */
+#define GX_RESULT_INT64 0
+#define GX_RESULT_UINT64 1
+#define GX_RESULT_FP64 2
+int gx_result_write(const char *path, int kind, const uint64_t *ids, const void *values, uint64_t n,
+                    const uint64_t *value_map);
+
+/* ---- load stage -------------------------------------------------------------------------
+ * Replaces bin/py/relabel.py:8-79 (DuckDB joins) in bin/sh/load-graph.sh:49-60: X.v / X.e -> out_dir/graph.vtx (original id
+ * of dense vertex k on line k, .v row order) and out_dir/graph.mtx (banner, `%%GraphBLAS GrB_BOOL|GrB_FP64`, `n n nnz`,
+ * 1-based `src dst val` in .e order; weights kept as the text they came as).  Parsing, id lookup and formatting run on all
+ * host threads; host-only.  bin/py/relabel.py of this repo is the same-flags front-end. */
+int gx_relabel(const char *vertex_path, const char *edge_path, const char *out_dir, int weighted, int directed,
+               uint64_t *n_out, uint64_t *nnz_out);
 
 /* ---- synthetic inputs ----------------------------------------------------
  * Graph500 RMAT (0.57,0.19,0.19,0.05), `edgefactor` * 2^scale generated edges, counter-based

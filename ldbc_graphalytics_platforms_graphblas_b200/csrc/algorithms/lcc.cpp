@@ -5,20 +5,18 @@
 
 #include "cli_common.h"
 
-void SerializeLCCResult(const std::vector<double> &lcc, const std::vector<GrB_Index> &mapping,
+void SerializeLCCResult(const PinnedVector<double> &lcc, const std::vector<GrB_Index> &mapping,
                         const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
     // vertices LAGraph leaves without an entry are written as 0.0 (lcc.cpp:49-54); gx_lcc returns 0.0 for them
-    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_sci(mapping[v], lcc[v]);
+    file.lines_sci(mapping.data(), lcc.data(), mapping.size());
 }
 
-std::vector<double> LA_LCC(gx_graph *G, GrB_Index n)
+void LA_LCC(gx_graph *G, PinnedVector<double> &lcc)
 {
     ComputationTimer timer{"LCC"};
-    std::vector<double> lcc(n);
     OK(gx_lcc(G, lcc.data()));
-    return lcc;
 }
 
 int main(int argc, char **argv)
@@ -28,9 +26,11 @@ int main(int argc, char **argv)
     HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
+    ReserveForGraph(A);
     gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    PinnedVector<double> result(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
-    std::vector<double> result = LA_LCC(G, A.nrows);
+    LA_LCC(G, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
 
     SerializeLCCResult(result, mapping, parameters);

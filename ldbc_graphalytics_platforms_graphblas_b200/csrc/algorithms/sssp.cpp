@@ -6,22 +6,17 @@
 
 #include "cli_common.h"
 
-void SerializeSSSPResult(const std::vector<double> &dist, const std::vector<GrB_Index> &mapping,
+void SerializeSSSPResult(const PinnedVector<double> &dist, const std::vector<GrB_Index> &mapping,
                          const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
-    for (GrB_Index v = 0; v < mapping.size(); v++) {
-        if (std::isinf(dist[v])) file.line_text(mapping[v], "infinity"); // sssp.cpp:41-46
-        else file.line_sci(mapping[v], dist[v]);
-    }
+    file.lines_sci(mapping.data(), dist.data(), mapping.size()); // +inf is written as `infinity` (sssp.cpp:41-46)
 }
 
-std::vector<double> LA_SSSP(gx_graph *G, GrB_Index sourceVertex, GrB_Index n)
+void LA_SSSP(gx_graph *G, GrB_Index sourceVertex, PinnedVector<double> &dist)
 {
     ComputationTimer timer{"SSSP"};
-    std::vector<double> dist(n);
     OK(gx_sssp(G, sourceVertex, dist.data()));
-    return dist;
 }
 
 int main(int argc, char **argv)
@@ -39,9 +34,11 @@ int main(int argc, char **argv)
     const GrB_Index sourceVertex = (GrB_Index)std::distance(mapping.begin(), it);
     if (A.iso) throw std::runtime_error("SSSP needs a weighted graph (graph.mtx of type real)");
 
+    ReserveForGraph(A);
     gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    PinnedVector<double> result(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
-    std::vector<double> result = LA_SSSP(G, sourceVertex, A.nrows);
+    LA_SSSP(G, sourceVertex, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
 
     SerializeSSSPResult(result, mapping, parameters);

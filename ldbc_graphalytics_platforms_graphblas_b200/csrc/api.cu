@@ -111,6 +111,10 @@ extern "C" int gx_init(int device)
         Context &c = ctx();
         if (c.ready && c.device == device) return;
         if (c.ready) throw Error(GX_ERR_INVALID, "context already bound to another device");
+        // one fresh process per job (GraphblasJob.java:70-97): load every kernel of the library now, with the context,
+        // instead of lazily at its first launch inside an algorithm's timed window (has no effect once the CUDA
+        // runtime is up, e.g. under a host that initialised it before; an explicit setting wins)
+        setenv("CUDA_MODULE_LOADING", "EAGER", 0);
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0) {
@@ -138,6 +142,26 @@ extern "C" int gx_init(int device)
         GX_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
         c.device = device;
         c.ready = true;
+    });
+}
+
+// Grows the stream-ordered memory pool to `bytes` ahead of time (allocate + free; the release threshold keeps the
+// memory in the pool), so that the algorithms' scratch buffers are served from the pool instead of being mapped on
+// first use.  Resource allocation, not computation: the analogue of sizing a memory pool at start-up.
+extern "C" int gx_reserve(uint64_t bytes)
+{
+    return guarded([&] {
+        require_ready();
+        Context &c = ctx();
+        size_t free_b = 0, total_b = 0;
+        GX_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t cap = (uint64_t)(free_b * 0.6);
+        if (bytes > cap) bytes = cap;
+        if (!bytes) return;
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, bytes, c.stream) != cudaSuccess) { cudaGetLastError(); return; } // best effort
+        GX_CUDA(cudaFreeAsync(p, c.stream));
+        GX_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
 
@@ -255,6 +279,25 @@ extern "C" int gx_host_free(void *p)
 }
 
 extern "C" void gx_free_host(void *p) { free(p); }
+
+// Page-locks a host array the caller already owns (e.g. the CSR arrays a loader filled), so that the upload that
+// follows runs at PCIe speed without a pageable staging copy.  Best effort: a failure leaves the memory pageable.
+extern "C" int gx_host_register(const void *p, uint64_t bytes)
+{
+    return guarded([&] {
+        require_ready();
+        if (!p || !bytes) return;
+        if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError();
+    });
+}
+
+extern "C" int gx_host_unregister(const void *p)
+{
+    return guarded([&] {
+        if (!p) return;
+        if (cudaHostUnregister(const_cast<void *>(p)) != cudaSuccess) cudaGetLastError();
+    });
+}
 
 // ------------------------------------------------------------------------- NCCL
 extern "C" int gx_comm_unique_id(void *id128)

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cinttypes>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -468,8 +469,238 @@ void ResultWriter::line_sci(GrB_Index id, double v)
     used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %.16e\n", id, v);
 }
 
+// decimal digits of v at dst (no terminator); returns the length
+static inline size_t put_u64(char *dst, uint64_t v)
+{
+    char tmp[24];
+    size_t k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (size_t i = 0; i < k; i++) dst[i] = tmp[k - 1 - i];
+    return k;
+}
+
+template <class F>
+void ResultWriter::lines_parallel(GrB_Index n, F &&one)
+{
+    flush();
+    const GrB_Index SUPER = GrB_Index(1) << 23; // lines per round: bounds the buffers to ~0.5 GB whatever n is
+    const unsigned T = loader_threads((size_t)std::min<GrB_Index>(n, SUPER), 1u << 14);
+    std::vector<std::vector<char>> out(T);
+    for (GrB_Index base = 0; base < n; base += SUPER) {
+        const GrB_Index cnt = std::min<GrB_Index>(SUPER, n - base);
+        run_parallel(T, [&](unsigned t) {
+            const GrB_Index a = base + cnt * t / T, b = base + cnt * (t + 1) / T;
+            std::vector<char> &o = out[t];
+            o.resize((size_t)(b - a) * 64); // a line is at most 20 + 1 + 24 + 1 bytes
+            size_t used = 0;
+            for (GrB_Index i = a; i < b; i++) used += one(o.data() + used, i);
+            o.resize(used);
+        });
+        for (unsigned t = 0; t < T; t++)
+            if (!out[t].empty()) fwrite(out[t].data(), 1, out[t].size(), f_);
+    }
+}
+
+void ResultWriter::lines_int(const GrB_Index *ids, const int64_t *vals, GrB_Index n)
+{
+    lines_parallel(n, [&](char *dst, GrB_Index i) {
+        size_t k = put_u64(dst, ids[i]);
+        dst[k++] = ' ';
+        int64_t v = vals[i];
+        if (v < 0) { dst[k++] = '-'; k += put_u64(dst + k, (uint64_t)0 - (uint64_t)v); }
+        else k += put_u64(dst + k, (uint64_t)v);
+        dst[k++] = '\n';
+        return k;
+    });
+}
+
+void ResultWriter::lines_uint(const GrB_Index *ids, const uint64_t *vals, GrB_Index n, const GrB_Index *map)
+{
+    lines_parallel(n, [&](char *dst, GrB_Index i) {
+        size_t k = put_u64(dst, ids[i]);
+        dst[k++] = ' ';
+        k += put_u64(dst + k, map ? map[vals[i]] : vals[i]);
+        dst[k++] = '\n';
+        return k;
+    });
+}
+
+void ResultWriter::lines_ids(const GrB_Index *ids, GrB_Index n)
+{
+    lines_parallel(n, [&](char *dst, GrB_Index i) {
+        size_t k = put_u64(dst, ids[i]);
+        dst[k++] = '\n';
+        return k;
+    });
+}
+
+void ResultWriter::lines_sci(const GrB_Index *ids, const double *vals, GrB_Index n)
+{
+    lines_parallel(n, [&](char *dst, GrB_Index i) {
+        size_t k = put_u64(dst, ids[i]);
+        dst[k++] = ' ';
+        const double v = vals[i];
+        if (v == HUGE_VAL) { memcpy(dst + k, "infinity", 8); k += 8; }
+        else k += (size_t)snprintf(dst + k, 32, "%.16e", v);
+        dst[k++] = '\n';
+        return k;
+    });
+}
+
 void ResultWriter::line_text(GrB_Index id, const char *s)
 {
     if (used_ + 64 > buf_.size()) flush();
     used_ += (size_t)snprintf(buf_.data() + used_, 64, "%" PRIu64 " %s\n", id, s);
+}
+
+// ------------------------------------------------------------------------- relabel (.v/.e -> graph.vtx/graph.mtx)
+// The load stage the reference runs through DuckDB (bin/py/relabel.py:8-79, bin/sh/load-graph.sh:49-60): vertex ids
+// of X.v become dense ids in .v row order, every edge of X.e is rewritten with 1-based dense endpoints, and the two
+// text files the converter / the loaders read are written.  Everything -- parsing both files in byte ranges, the
+// id lookup, formatting -- runs on all host threads; edge weights are carried as the text they came as, so they
+// round-trip byte for byte.
+namespace {
+
+struct Span { const char *p; uint32_t len; };
+
+// lines of [begin, end) -> callback(line_begin, line_end) for every non-empty line; ranges start at line starts
+template <class F>
+void for_each_line(const char *q, const char *stop, F &&f)
+{
+    while (q < stop) {
+        const char *e = q;
+        while (e < stop && *e != '\n') e++;
+        const char *le = e;
+        while (le > q && (le[-1] == '\r' || le[-1] == ' ' || le[-1] == '\t')) le--;
+        if (le > q) f(q, le);
+        q = e < stop ? e + 1 : stop;
+    }
+}
+
+std::vector<const char *> line_cuts(const char *body, const char *end, unsigned T)
+{
+    std::vector<const char *> cut(T + 1);
+    cut[0] = body;
+    cut[T] = end;
+    for (unsigned t = 1; t < T; t++) {
+        const char *q = body + (size_t)(end - body) * t / T;
+        while (q < end && *q != '\n') q++;
+        cut[t] = q < end ? q + 1 : end;
+        if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    }
+    return cut;
+}
+
+} // namespace
+
+void RelabelGraph(const std::string &vertex_path, const std::string &edge_path, const std::string &out_dir, bool weighted,
+                  bool directed, GrB_Index *n_out, GrB_Index *nnz_out)
+{
+    // ---- X.v: one original id per line
+    std::vector<GrB_Index> ids;
+    {
+        FileBytes vf(vertex_path);
+        const char *body = vf.data.data(), *end = body + vf.data.size() - 1;
+        const unsigned T = loader_threads((size_t)(end - body), 1u << 20);
+        const std::vector<const char *> cut = line_cuts(body, end, T);
+        std::vector<std::vector<GrB_Index>> part(T);
+        run_parallel(T, [&](unsigned t) {
+            part[t].reserve((size_t)(cut[t + 1] - cut[t]) / 8 + 16);
+            for_each_line(cut[t], cut[t + 1], [&](const char *a, const char *) { const char *q = a; part[t].push_back(parse_u64(q)); });
+        });
+        size_t total = 0;
+        std::vector<size_t> off(T + 1, 0);
+        for (unsigned t = 0; t < T; t++) { total += part[t].size(); off[t + 1] = total; }
+        ids.resize(total);
+        run_parallel(T, [&](unsigned t) { std::copy(part[t].begin(), part[t].end(), ids.begin() + off[t]); });
+    }
+    const GrB_Index n = ids.size();
+    if (n >= 0xFFFFFFFEull) throw std::runtime_error("More than 2^32 - 2 vertices are not supported");
+    // lookup id -> row: the ids themselves when the file is ascending (Graphalytics' .v files are), else a sorted copy
+    bool ascending = true;
+    for (GrB_Index i = 1; i < n && ascending; i++) ascending = ids[i] > ids[i - 1];
+    std::vector<GrB_Index> sorted_ids;
+    std::vector<uint32_t> sorted_row;
+    if (!ascending) {
+        sorted_row.resize(n);
+        std::iota(sorted_row.begin(), sorted_row.end(), 0u);
+        std::sort(sorted_row.begin(), sorted_row.end(), [&](uint32_t a, uint32_t b) { return ids[a] < ids[b]; });
+        sorted_ids.resize(n);
+        for (GrB_Index i = 0; i < n; i++) sorted_ids[i] = ids[sorted_row[i]];
+    }
+    const std::vector<GrB_Index> &keys = ascending ? ids : sorted_ids;
+    auto dense = [&](GrB_Index id) -> uint32_t {
+        const auto it = std::lower_bound(keys.begin(), keys.end(), id);
+        if (it == keys.end() || *it != id) throw std::runtime_error("edge endpoint " + std::to_string(id) + " is not in the vertex file");
+        const size_t pos = (size_t)(it - keys.begin());
+        return ascending ? (uint32_t)pos : sorted_row[pos];
+    };
+    // ---- X.e: `src dst[ weight]`, parsed and relabelled in one pass
+    FileBytes ef(edge_path);
+    const char *ebody = ef.data.data(), *eend = ebody + ef.data.size() - 1;
+    const unsigned T = loader_threads((size_t)(eend - ebody), 4u << 20);
+    const std::vector<const char *> cut = line_cuts(ebody, eend, T);
+    struct Part { std::vector<uint32_t> src, dst; std::vector<Span> w; };
+    std::vector<Part> part(T);
+    run_parallel(T, [&](unsigned t) {
+        Part &o = part[t];
+        const size_t guess = (size_t)(cut[t + 1] - cut[t]) / 12 + 16;
+        o.src.reserve(guess);
+        o.dst.reserve(guess);
+        if (weighted) o.w.reserve(guess);
+        for_each_line(cut[t], cut[t + 1], [&](const char *a, const char *le) {
+            const char *q = a;
+            const GrB_Index s = parse_u64(q), d = parse_u64(q);
+            o.src.push_back(dense(s));
+            o.dst.push_back(dense(d));
+            if (weighted) {
+                q = skip_ws(q);
+                if (q >= le) throw std::runtime_error("edge without a weight in a weighted edge file");
+                o.w.push_back(Span{q, (uint32_t)(le - q)});
+            }
+        });
+    });
+    GrB_Index nnz = 0;
+    for (unsigned t = 0; t < T; t++) nnz += part[t].src.size();
+    // ---- graph.vtx: the ids in .v row order
+    {
+        ResultWriter vtx(out_dir + "/graph.vtx");
+        if (!vtx.ok()) throw std::runtime_error("Cannot create " + out_dir + "/graph.vtx");
+        vtx.lines_ids(ids.data(), n);
+    }
+    // ---- graph.mtx (relabel.py:64-79): banner, GraphBLAS type line, `n n nnz`, then 1-based `src dst val` in .e order
+    FILE *f = fopen((out_dir + "/graph.mtx").c_str(), "w");
+    if (!f) throw std::runtime_error("Cannot create " + out_dir + "/graph.mtx");
+    fprintf(f, "%%%%MatrixMarket matrix coordinate %s %s\n%%%%GraphBLAS %s\n%" PRIu64 " %" PRIu64 " %" PRIu64 "\n",
+            weighted ? "real" : "integer", directed ? "general" : "symmetric", weighted ? "GrB_FP64" : "GrB_BOOL", n, n, nnz);
+    std::vector<std::vector<char>> out(T);
+    std::exception_ptr err;
+    try {
+        run_parallel(T, [&](unsigned t) {
+            const Part &o = part[t];
+            std::vector<char> &b = out[t];
+            size_t need = o.src.size() * 24;
+            if (weighted) for (const Span &x : o.w) need += x.len;
+            b.resize(need);
+            size_t k = 0;
+            for (size_t i = 0; i < o.src.size(); i++) {
+                k += put_u64(b.data() + k, (uint64_t)o.src[i] + 1);
+                b[k++] = ' ';
+                k += put_u64(b.data() + k, (uint64_t)o.dst[i] + 1);
+                b[k++] = ' ';
+                if (weighted) { memcpy(b.data() + k, o.w[i].p, o.w[i].len); k += o.w[i].len; }
+                else b[k++] = '1';
+                b[k++] = '\n';
+            }
+            b.resize(k);
+        });
+        for (unsigned t = 0; t < T; t++)
+            if (!out[t].empty() && fwrite(out[t].data(), 1, out[t].size(), f) != out[t].size()) throw std::runtime_error("Write failed: graph.mtx");
+    } catch (...) {
+        err = std::current_exception();
+    }
+    fclose(f);
+    if (err) std::rethrow_exception(err);
+    if (n_out) *n_out = n;
+    if (nnz_out) *nnz_out = nnz;
 }

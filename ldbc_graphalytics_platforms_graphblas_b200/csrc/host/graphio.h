@@ -35,6 +35,10 @@ std::vector<GrB_Index> ReadVtxFile(const std::string &path);
 std::vector<GrB_Index> ReadVtbFile(const std::string &path);
 void WriteVtbFile(const std::string &path, const std::vector<GrB_Index> &mapping);
 
+// X.v / X.e -> out_dir/graph.vtx + out_dir/graph.mtx (bin/py/relabel.py:8-79), on all host threads
+void RelabelGraph(const std::string &vertex_path, const std::string &edge_path, const std::string &out_dir, bool weighted,
+                  bool directed, GrB_Index *n_out, GrB_Index *nnz_out);
+
 // Buffered "<original id> <value>\n" writer shared by the six Serialize*Result functions.
 class ResultWriter {
     FILE *f_ = nullptr;
@@ -53,4 +57,16 @@ class ResultWriter {
     void line_uint(GrB_Index id, uint64_t v);
     void line_sci(GrB_Index id, double v);      // precision(16) << scientific
     void line_text(GrB_Index id, const char *s);
+    // Whole-vector forms: the n lines are formatted on all host threads (a block of consecutive lines per thread into
+    // a buffer of its own) and written out in order -- 33 M lines of "%.16e" text are seconds of snprintf on one core.
+    // ids[i] is the vertex id of line i.  lines_uint: the value is map[vals[i]] when map is given (cdlp.cpp:48).
+    // lines_sci: +inf is written as the literal `infinity` (sssp.cpp:41-46).
+    void lines_int(const GrB_Index *ids, const int64_t *vals, GrB_Index n);
+    void lines_uint(const GrB_Index *ids, const uint64_t *vals, GrB_Index n, const GrB_Index *map = nullptr);
+    void lines_sci(const GrB_Index *ids, const double *vals, GrB_Index n);
+    void lines_ids(const GrB_Index *ids, GrB_Index n); // one id per line (graph.vtx)
+
+  private:
+    template <class F>
+    void lines_parallel(GrB_Index n, F &&one);
 };

@@ -146,3 +146,80 @@ def test_validator_rules():
     assert validator.validate("pr", [1.0, 2.00001], [1.0, 2.0]) and not validator.validate("pr", [1.0, 2.001], [1.0, 2.0])
     assert validator.validate("sssp", [np.inf, 1.0], [np.inf, 1.0]) and not validator.validate("sssp", [5.0, 1.0], [np.inf, 1.0])
     assert np.array_equal(validator.canonical_min_labels([7, 7, 3, 3, 7]), [0, 0, 2, 2, 0])
+
+
+def test_result_writer_matches_the_reference_format(tmp_path):
+    """gx_result_write (the six Serialize*Result functions, formatted on all host threads): byte-identical to
+    `<id> <value>` lines with int64 / uint64 in decimal and precision(16) << scientific doubles, `infinity` for +inf
+    (bfs.cpp:59-63, pr.cpp:27-28, sssp.cpp:41-46, cdlp.cpp:48)."""
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    rng = np.random.default_rng(9)
+    n = 200_003                                      # several thread blocks, not a multiple of anything
+    ids = np.sort(rng.choice(10**12, n, replace=False)).astype(np.uint64)
+    lv = rng.integers(0, 50, n).astype(np.int64)
+    lv[::7] = np.iinfo(np.int64).max                 # unreached
+    lv[3] = -5                                       # (never produced, but the formatter must not mangle it)
+    p = tmp_path / "bfs"
+    capi.write_result(str(p), ids, lv)
+    assert p.read_text() == "".join(f"{i} {v}\n" for i, v in zip(ids.tolist(), lv.tolist()))
+    lab = rng.integers(0, n, n).astype(np.uint64)
+    capi.write_result(str(p), ids, lab, value_map=ids)
+    assert p.read_text() == "".join(f"{i} {ids[v]}\n" for i, v in zip(ids.tolist(), lab.tolist()))
+    capi.write_result(str(p), ids, lab)
+    assert p.read_text() == "".join(f"{i} {v}\n" for i, v in zip(ids.tolist(), lab.tolist()))
+    x = rng.random(n) * 10.0 ** rng.integers(-300, 300, n)
+    x[::5] = 0.0
+    x[1::11] = np.inf
+    x[2] = 1.0
+    capi.write_result(str(p), ids, x)
+    want = "".join(f"{i} {'infinity' if np.isinf(v) else '%.16e' % v}\n" for i, v in zip(ids.tolist(), x.tolist()))
+    assert p.read_text() == want
+    capi.write_result(str(p), ids[:0], x[:0])
+    assert p.read_text() == ""
+
+
+def test_relabel_at_scale_and_edge_cases(tmp_path):
+    """gx_relabel on a generated edge list (RMAT-18: 4 M lines), byte for byte against the lines the reference's
+    relabel.py:64-79 would write; a vertex file that is NOT ascending; an endpoint missing from the vertex file."""
+    import time
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    src, dst = rmat.rmat_edges(18)
+    ids = np.unique(np.concatenate([src, dst]))
+    w = rmat.edge_weights(src, dst, 7)
+    vp, ep = tmp_path / "g.v", tmp_path / "g.e"
+    np.savetxt(vp, ids, fmt="%d")
+    wtxt = np.char.mod("%.17g", w)
+    with open(ep, "w") as f:
+        f.write("\n".join(" ".join(t) for t in zip(src.astype(str), dst.astype(str), wtxt)) + "\n")
+    out = tmp_path / "out"
+    t0 = time.perf_counter()
+    n, nnz = capi.relabel(str(vp), str(ep), str(out), True, True)
+    dt = time.perf_counter() - t0
+    assert (n, nnz) == (ids.size, src.size)
+    assert dt < 20, f"relabelling 4 M edges took {dt:.1f}s"
+    lines = open(out / "graph.mtx").read().split("\n")
+    assert lines[:3] == ["%%MatrixMarket matrix coordinate real general", "%%GraphBLAS GrB_FP64", f"{n} {n} {nnz}"]
+    s = np.searchsorted(ids, src) + 1
+    d = np.searchsorted(ids, dst) + 1
+    for k in (0, 1, 12345, nnz // 2, nnz - 1):
+        assert lines[3 + k] == f"{s[k]} {d[k]} {wtxt[k]}"
+    assert len(lines) == 3 + nnz + 1 and lines[-1] == ""
+    assert np.array_equal(np.loadtxt(out / "graph.vtx", dtype=np.uint64), ids)
+    # a shuffled vertex file: dense ids follow the file's row order, not the id order
+    perm = np.random.default_rng(1).permutation(ids.size)
+    np.savetxt(vp, ids[perm], fmt="%d")
+    with open(ep, "w") as f:
+        f.write("\n".join(f"{a} {b}" for a, b in zip(src[:1000], dst[:1000])) + "\n")
+    n2, nnz2 = capi.relabel(str(vp), str(ep), str(out), False, False)
+    assert (n2, nnz2) == (ids.size, 1000)
+    lines = open(out / "graph.mtx").read().split("\n")
+    assert lines[0] == "%%MatrixMarket matrix coordinate integer symmetric" and lines[1] == "%%GraphBLAS GrB_BOOL"
+    row_of = np.empty(ids.size, dtype=np.int64)
+    row_of[perm] = np.arange(ids.size)
+    for k in (0, 17, 999):
+        assert lines[3 + k] == f"{row_of[np.searchsorted(ids, src[k])] + 1} {row_of[np.searchsorted(ids, dst[k])] + 1} 1"
+    assert np.array_equal(np.loadtxt(out / "graph.vtx", dtype=np.uint64), ids[perm])
+    with open(ep, "w") as f:
+        f.write(f"{ids[0]} {int(ids.max()) + 12345}\n")
+    with pytest.raises(capi.GxError):
+        capi.relabel(str(vp), str(ep), str(out), False, True)
