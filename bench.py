@@ -317,6 +317,28 @@ def run_gpu(args):
                        "all-gathers the rest over NVLink; rank 0 reads the results back"),
            "steps": e2e_steps, "breakdown_ms": {k: round(v, 3) for k, v in e2e_parts.items()}}
 
+    # ---- the same through the GrB_Index route of INTEGRATION.md B: 8-byte column ids handed to gx_graph_create_csr (what
+    # GxB_Matrix_export_CSR gives a reference-side binding), narrowed on the device; twice the H2D bytes
+    if world == 1:
+        pin_ci64 = capi.PinnedArray((m,), np.uint64); pin_ci64.array[:] = ci_h
+
+        def e2e64_step():
+            h = capi.Graph.from_csr(n, pin_rp.array, pin_ci64.array, None, True, cache=capi.GX_CACHE_AT)
+            h.bfs(src, out=pin_lvl.array)
+            h.pagerank(PR_DAMPING, PR_ITERS, out=pin_rank.array)
+            h.free()
+        e2e64_step()
+        capi.sync()
+        t1 = time.perf_counter()
+        for _ in range(3):
+            e2e64_step()
+        capi.sync()
+        t64 = (time.perf_counter() - t1) / 3
+        e2e["grb_index_route"] = {"value": 2 * ev / t64, "ms_per_step": 1e3 * t64, "h2d_bytes_per_step": int(8 * (n + 1) + 8 * m),
+                                  "entry": "gx_graph_create_csr (uint64 column ids) + gx_graph_cache(GX_CACHE_AT) + gx_bfs + gx_pagerank + gx_graph_free",
+                                  "steps": 3}
+        pin_ci64.free()
+
     # ---- the reference's own window on the device (pr.cpp:58-61: transpose + out-degree INSIDE PageRank's window;
     # bfs.cpp:79-80: nothing cached, LAGraph runs push-only): the graph is resident but nothing derived from it is,
     # i.e. what the drop-in binaries time between their two Processing lines

@@ -13,8 +13,10 @@
 //
 //   k_lcc_count   8-lane group per oriented entry: lanes stride the shorter list and look each
 //                 element up in the longer one -- through the row's membership table (open
-//                 addressing, 4 slots per entry, built once per graph: 1-2 probes in one cache line)
-//                 or, for rows under 16 entries, by binary search
+//                 addressing, 4 slots per entry, built once per graph) or, for rows under 16 entries,
+//                 by binary search.  The entries are ordered by the owner of the longer list; a CTA
+//                 copies an owner's table (<= 32 KB: every table on RMAT-22, where the largest
+//                 oriented row has 1048 entries) into shared memory and serves the whole segment from it
 //   k_lcc_final   lcc = num / (d (d-1))
 // Algorithmic bytes: 4m + 8(n+1) + 4*sum_{u->v}(d+(u) + d+(v)) + 8n.
 #include <cstdlib>
@@ -27,82 +29,115 @@ constexpr int LCC_G = 8;
 constexpr uint32_t LCC_RUN = 1024; // entries a CTA draws at a time (32 trips of its 32 groups; 64 / 256 / 1024 / 4096: 85 / 77 / 74.5 / 76 ms)
 constexpr uint32_t IDMASK = ~LCC_MULT_BIT;
 
-__global__ void __launch_bounds__(256)
-k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ eu,
-            const uint32_t *__restrict__ ev, const uint64_t *__restrict__ tab_off, const uint32_t *__restrict__ tab, uint64_t e0, uint64_t om,
-            uint32_t run, unsigned long long *__restrict__ next_run, unsigned long long *__restrict__ num)
+constexpr uint32_t LCC_SMEM_SLOTS = 8192; // membership tables up to this many slots (32 KB) are staged in shared memory
+
+// One intersection: the lanes of an 8-lane group stride the shorter list [sa, sb) and look every element up in the
+// longer row's membership table -- TAB_SMEM: the CTA's shared-memory copy of it (0.27 LSU wavefronts per probe instead
+// of one: the run's probes are ~200x the table's size), else in global memory; rows under LCC_TAB_MIN entries have no
+// table and are searched.  Adds the corner counts of the common neighbours, returns this lane's share for u and v.
+template <bool TAB_SMEM>
+__device__ __forceinline__ void lcc_intersect(const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ tab, const uint32_t *s_tab,
+                                              uint64_t sa, uint64_t sb, uint64_t la, uint64_t lb, uint64_t t0, uint64_t tmask,
+                                              unsigned sub, bool u_short, unsigned long long m_uv, unsigned long long *__restrict__ num,
+                                              unsigned long long &su, unsigned long long &sv)
 {
-    // oriented entries [e0, om) are this rank's share.  A CTA draws runs of LCC_RUN consecutive entries
-    // from a counter: consecutive entries share the owner of the longer list, so the CTA probes one
-    // membership table for a while (L1 hits) and the draw balances the load whatever a run costs.
+    for (uint64_t i = sa + sub; i < sb; i += LCC_G) {
+        const uint32_t cs = ocol[i];
+        const uint32_t w = cs & IDMASK;
+        uint32_t cl = 0xFFFFFFFFu; // the longer list's entry for w, if any
+        if (tmask) {
+            // open addressing at load 1/4: a miss ends after 1.4 probes on average, all in one line
+            uint64_t sl = lcc_tab_hash(w, tmask);
+            for (;;) {
+                const uint32_t c = TAB_SMEM ? s_tab[sl] : tab[t0 + sl];
+                if (c == 0xFFFFFFFFu || (c & IDMASK) == w) { cl = c; break; }
+                sl = (sl + 1) & (tmask - 1);
+            }
+        } else {
+            uint64_t lo = la, hi = lb;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if ((ocol[mid] & IDMASK) < w) lo = mid + 1; else hi = mid;
+            }
+            if (lo < lb) cl = ocol[lo];
+        }
+        if (cl != 0xFFFFFFFFu && (cl & IDMASK) == w) {
+            const unsigned long long m_s = (cs & LCC_MULT_BIT) ? 2ull : 1ull; // side (short owner, w)
+            const unsigned long long m_l = (cl & LCC_MULT_BIT) ? 2ull : 1ull; // side (long owner, w)
+            // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v)
+            su += u_short ? m_l : m_s;
+            sv += u_short ? m_s : m_l;
+            atomicAdd(&num[w], m_uv);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 6)
+k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ eu,
+            const uint32_t *__restrict__ ev, const uint32_t *__restrict__ eowner, const uint64_t *__restrict__ tab_off,
+            const uint32_t *__restrict__ tab, uint64_t e0, uint64_t om, uint32_t run, unsigned long long *__restrict__ next_run,
+            unsigned long long *__restrict__ num)
+{
+    // oriented entries [e0, om) are this rank's share, ordered by the owner of the longer list of their intersection.
+    // A CTA draws runs of `run` consecutive entries from a counter (the draw balances the load whatever a run costs) and
+    // walks a run segment by segment -- a segment = the consecutive entries of one owner: the owner's membership table
+    // is copied into shared memory once and every probe of the segment hits that copy.
+    extern __shared__ uint32_t s_tab[];
     const unsigned sub = threadIdx.x & (LCC_G - 1), grp = threadIdx.x / LCC_G;
     __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_seg_end;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_base = atomicAdd(next_run, (unsigned long long)run);
         __syncthreads();
         const uint64_t base = e0 + s_base;
         if (base >= om) break;
-      for (uint32_t r = grp; r < run; r += 256 / LCC_G) {
-        const uint64_t gi = base + r;
-        unsigned long long su = 0, sv = 0;
-        uint32_t u = 0, v = 0;
-        const bool live = gi < om;
-        if (live) {
-            u = eu[gi]; // entries in the order of the longer list's owner (graph.cu)
-            const uint32_t cv = ev[gi];
-            v = cv & IDMASK;
-            const unsigned long long m_uv = (cv & LCC_MULT_BIT) ? 2ull : 1ull;
-            uint64_t ua = orp[u], ub = orp[u + 1], va = orp[v], vb = orp[v + 1];
-            // lanes walk the shorter list (sa..sb), search the longer one (la..lb)
-            const bool u_short = (ub - ua) <= (vb - va);
-            const uint64_t sa = u_short ? ua : va, sb = u_short ? ub : vb;
-            const uint64_t la = u_short ? va : ua, lb = u_short ? vb : ub;
-            // the longer list's membership table, if it has one (rows from LCC_TAB_MIN entries on)
-            const uint32_t owner = u_short ? v : u;
-            const uint64_t t0 = tab_off[owner], tmask = tab_off[owner + 1] - t0; // size (power of two) or 0
-            for (uint64_t i = sa + sub; i < sb; i += LCC_G) {
-                const uint32_t cs = ocol[i];
-                const uint32_t w = cs & IDMASK;
-                uint32_t cl = 0xFFFFFFFFu; // the longer list's entry for w, if any
-                if (tmask) {
-                    // open addressing at load 1/4: a miss ends after 1.4 probes on average, all in one line
-                    uint64_t sl = lcc_tab_hash(w, tmask);
-                    for (;;) {
-                        const uint32_t c = tab[t0 + sl];
-                        if (c == 0xFFFFFFFFu || (c & IDMASK) == w) { cl = c; break; }
-                        sl = (sl + 1) & (tmask - 1);
-                    }
-                } else {
-                    uint64_t lo = la, hi = lb;
-                    while (lo < hi) {
-                        const uint64_t mid = (lo + hi) >> 1;
-                        if ((ocol[mid] & IDMASK) < w) lo = mid + 1; else hi = mid;
-                    }
-                    if (lo < lb) cl = ocol[lo];
+        const uint64_t run_end = base + run < om ? base + run : om;
+        uint64_t pos = base;
+        while (pos < run_end) {
+            // ---- the segment [pos, seg_end) of the owner of entry `pos` (owners ascend along the list)
+            const uint32_t owner = eowner[pos];
+            if (threadIdx.x == 0) s_seg_end = run_end;
+            __syncthreads();
+            for (uint64_t i = pos + 1 + threadIdx.x; i < run_end; i += 256)
+                if (eowner[i] != owner) { atomicMin(&s_seg_end, (unsigned long long)i); break; }
+            const uint64_t t0 = tab_off[owner], tmask = tab_off[owner + 1] - t0; // table size (power of two) or 0
+            const bool staged = tmask != 0 && tmask <= LCC_SMEM_SLOTS;
+            if (staged)
+                for (uint32_t i = threadIdx.x; i < (uint32_t)tmask; i += 256) s_tab[i] = tab[t0 + i];
+            __syncthreads();
+            const uint64_t seg_end = s_seg_end;
+            for (uint64_t r0 = pos; r0 < seg_end; r0 += 256 / LCC_G) { // same trip count for all groups of a warp
+                const uint64_t gi = r0 + grp;
+                unsigned long long su = 0, sv = 0;
+                uint32_t u = 0, v = 0;
+                const bool live = gi < seg_end;
+                if (live) {
+                    u = eu[gi];
+                    const uint32_t cv = ev[gi];
+                    v = cv & IDMASK;
+                    const unsigned long long m_uv = (cv & LCC_MULT_BIT) ? 2ull : 1ull;
+                    const uint64_t ua = orp[u], ub = orp[u + 1], va = orp[v], vb = orp[v + 1];
+                    // lanes walk the shorter list (sa..sb), look up in the longer one (la..lb) = the owner's
+                    const bool u_short = (ub - ua) <= (vb - va);
+                    const uint64_t sa = u_short ? ua : va, sb = u_short ? ub : vb;
+                    const uint64_t la = u_short ? va : ua, lb = u_short ? vb : ub;
+                    if (staged) lcc_intersect<true>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv);
+                    else lcc_intersect<false>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv);
                 }
-                {
-                    if (cl != 0xFFFFFFFFu && (cl & IDMASK) == w) {
-                        const unsigned long long m_s = (cs & LCC_MULT_BIT) ? 2ull : 1ull; // side (short owner, w)
-                        const unsigned long long m_l = (cl & LCC_MULT_BIT) ? 2ull : 1ull; // side (long owner, w)
-                        // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v)
-                        su += u_short ? m_l : m_s;
-                        sv += u_short ? m_s : m_l;
-                        atomicAdd(&num[w], m_uv);
-                    }
+#pragma unroll
+                for (int o = LCC_G / 2; o > 0; o >>= 1) {
+                    su += __shfl_xor_sync(FULL, su, o);
+                    sv += __shfl_xor_sync(FULL, sv, o);
+                }
+                if (live && sub == 0) {
+                    if (su) atomicAdd(&num[u], su);
+                    if (sv) atomicAdd(&num[v], sv);
                 }
             }
+            __syncthreads(); // the table copy is overwritten by the next segment
+            pos = seg_end;
         }
-#pragma unroll
-        for (int o = LCC_G / 2; o > 0; o >>= 1) {
-            su += __shfl_xor_sync(FULL, su, o);
-            sv += __shfl_xor_sync(FULL, sv, o);
-        }
-        if (live && sub == 0) {
-            if (su) atomicAdd(&num[u], su);
-            if (sv) atomicAdd(&num[v], sv);
-        }
-      }
     }
 }
 
@@ -138,14 +173,15 @@ extern "C" int gx_lcc(gx_graph *g, double *lcc_host)
             num.zero();
             next_run.zero();
             uint32_t run = LCC_RUN;
+            GX_CUDA(cudaFuncSetAttribute(k_lcc_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LCC_SMEM_SLOTS * sizeof(uint32_t))));
             // tuning knob; a multiple of 32 so that the four 8-lane groups of a warp make the same number of trips
             // (the shuffles inside the trip are warp-wide)
             if (const char *e = getenv("GX_LCC_RUN")) run = (uint32_t)atoi(e) >= 32 ? ((uint32_t)atoi(e) + 31u) & ~31u : 32;
             // the oriented entry list is split evenly over the ranks; corner counts are summed
             const Partition part = make_even_partition(g->om);
             if (part.hi > part.lo)
-                GX_LAUNCH(k_lcc_count, grid_persistent(8), 256, 0, g->orowptr.p, g->ocol.p, g->lcc_eu.p, g->lcc_ev.p, g->ltab_off.p, g->ltab.p, part.lo, part.hi,
-                          run, next_run.p, num.p);
+                GX_LAUNCH(k_lcc_count, grid_persistent(6), 256, LCC_SMEM_SLOTS * sizeof(uint32_t), g->orowptr.p, g->ocol.p, g->lcc_eu.p,
+                          g->lcc_ev.p, g->lcc_owner.p, g->ltab_off.p, g->ltab.p, part.lo, part.hi, run, next_run.p, num.p);
             allreduce(num.p, n, Dt::U64, Red::Sum);
             GX_LAUNCH(k_lcc_final, grid_persistent(8), 256, 0, num.p, g->udeg.p, n, g->res_f64.p);
         }

@@ -505,7 +505,7 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
     const double delta = sc.delta;
     DevBuf<unsigned long long> dist(n);
     DevBuf<uint32_t> state(n), stamp(n), q0(n), q1(n);
-    const uint64_t big_cap = m / CHUNK + m / 256 + 16; // pieces of one launch: ranges longer than 32 * 8 entries
+    const uint64_t big_cap = m / CHUNK + m / 128 + 16; // pieces of one launch: ranges longer than 32 * G entries, G >= 4
     DevBuf<uint32_t> big_row(big_cap);
     DevBuf<uint64_t> big_begin(big_cap), big_end(big_cap);
     DevBuf<SsspCounters> cnt(1);
@@ -518,6 +518,11 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
     uint64_t qn = 1;
     uint32_t epoch = 1;
     double T = delta;
+    // lanes per queue vertex (tuning knobs): light rows hold a handful of entries, whole rows a few dozen -- several
+    // vertices per warp keep more dependent row-offset -> entry -> distance chains in flight than one vertex per warp
+    int lg = 8, hg = 16;
+    if (const char *e = getenv("GX_SSSP_LG")) lg = atoi(e);
+    if (const char *e = getenv("GX_SSSP_HG")) hg = atoi(e);
     bool expanded = false; // some vertex was light-expanded since the last heavy phase
     for (;;) {
         // ---- light rounds: the bucket's members relax their light entries until nothing below T moves
@@ -526,9 +531,13 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
             GX_CUDA(cudaMemcpyAsync(qn_dev.p, &qn, sizeof(qn), cudaMemcpyHostToDevice, c.stream));
             GX_LAUNCH(k_sssp_clear, grid_for(qn, 256), 256, 0, queue, qn, state.p);
             // (grid capped: every warp ends with one atomic on the shared counters)
-            const unsigned g_light = grid_for(qn * 8, 256) < grid_persistent(8) ? grid_for(qn * 8, 256) : grid_persistent(8);
-            GX_LAUNCH((k_sssp_expand<8, false>), g_light, 256, 0, sc.lrowptr.p, sc.lcol.p, sc.lw.p, queue, qn_dev.p,
-                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), -1.0, nullptr);
+            const unsigned g_light = grid_for(qn * (unsigned)lg, 256) < grid_persistent(8) ? grid_for(qn * (unsigned)lg, 256) : grid_persistent(8);
+            if (lg == 4)
+                GX_LAUNCH((k_sssp_expand<4, false>), g_light, 256, 0, sc.lrowptr.p, sc.lcol.p, sc.lw.p, queue, qn_dev.p,
+                          dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), -1.0, nullptr);
+            else
+                GX_LAUNCH((k_sssp_expand<8, false>), g_light, 256, 0, sc.lrowptr.p, sc.lcol.p, sc.lw.p, queue, qn_dev.p,
+                          dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), -1.0, nullptr);
             GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.lcol.p, sc.lw.p, big_row.p, big_begin.p, big_end.p, dist.p,
                       state.p, cnt.p, bits(T), -1.0, nullptr);
             GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, state.p, 1u, n, next_q, &cnt.p->next_count);
@@ -544,8 +553,15 @@ static void sssp_delta_stepping(gx_graph *g, const SsspCache &sc, uint64_t src, 
         if (expanded) {
             cnt.zero();
             GX_LAUNCH(k_sssp_compact_eq, grid_persistent(8), 256, 0, stamp.p, epoch, n, next_q, &cnt.p->r_count);
-            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, rp, g->out.col.p, g->out.w.p, next_q, &cnt.p->r_count,
-                      dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, nullptr);
+            if (hg == 8)
+                GX_LAUNCH((k_sssp_expand<8, true>), grid_persistent(8), 256, 0, rp, g->out.col.p, g->out.w.p, next_q, &cnt.p->r_count,
+                          dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, nullptr);
+            else if (hg == 16)
+                GX_LAUNCH((k_sssp_expand<16, true>), grid_persistent(8), 256, 0, rp, g->out.col.p, g->out.w.p, next_q, &cnt.p->r_count,
+                          dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, nullptr);
+            else
+                GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, rp, g->out.col.p, g->out.w.p, next_q, &cnt.p->r_count,
+                          dist.p, state.p, stamp.p, epoch, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, nullptr);
             GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, g->out.col.p, g->out.w.p, big_row.p, big_begin.p, big_end.p, dist.p,
                       state.p, cnt.p, bits(T), delta, nullptr);
             // a heavy entry adds more than delta to a distance >= T - delta, so nothing lands below T;
@@ -656,7 +672,7 @@ static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uin
     unsigned long long *dist = (unsigned long long *)db.local;
     DevBuf<unsigned long long> ldone(own ? own : 1), hdone(own ? own : 1);
     DevBuf<uint32_t> queue(own + 1024);
-    const uint64_t big_cap = m / CHUNK + m / 256 + 16;
+    const uint64_t big_cap = m / CHUNK + m / 128 + 16;
     DevBuf<uint32_t> big_row(big_cap);
     DevBuf<uint64_t> big_begin(big_cap), big_end(big_cap);
     DevBuf<SsspCounters> cnt(1);
@@ -684,7 +700,7 @@ static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uin
         GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
         if (heavy) {
             GX_LAUNCH(k_sssp_m_build<true>, grid_persistent(8), 256, 0, dist, hdone.p, v0, v1, bits(T), queue.p, cnt.p);
-            GX_LAUNCH((k_sssp_expand<32, true>), grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue.p,
+            GX_LAUNCH((k_sssp_expand<16, true>), grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue.p,
                       &cnt.p->next_count, dist, nullptr, nullptr, 0u, big_row.p, big_begin.p, big_end.p, cnt.p, bits(T), delta, peers.p);
             GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, g->out.col.p, g->out.w.p, big_row.p, big_begin.p, big_end.p, dist,
                       nullptr, cnt.p, bits(T), delta, peers.p);

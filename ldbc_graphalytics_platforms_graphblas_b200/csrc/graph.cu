@@ -879,10 +879,14 @@ void ensure_lcc_cache(gx_graph *g)
         DevBuf<char> tmp2(tb2);
         GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, dk, dv, (int64_t)om, 0, bits_for(n), ctx().stream));
         GX_LAUNCH(k_lcc_permute, grid_persistent(8), 256, 0, dv.Current(), g->orow.p, g->ocol.p, om, g->lcc_eu.p, g->lcc_ev.p);
+        // the sorted keys are kept: the counting kernel finds the owner segments of a run by comparing them
+        g->lcc_owner.alloc(om);
+        GX_CUDA(cudaMemcpyAsync(g->lcc_owner.p, dk.Current(), om * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx().stream));
         GX_CUDA(cudaStreamSynchronize(ctx().stream)); // scoped sort buffers
     } else {
         g->lcc_eu.alloc(1);
         g->lcc_ev.alloc(1);
+        g->lcc_owner.alloc(1);
         g->ltab_off.alloc(n + 1);
         g->ltab_off.zero();
         g->ltab.alloc(1);

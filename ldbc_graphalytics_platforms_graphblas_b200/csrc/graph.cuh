@@ -82,6 +82,7 @@ struct gx_graph {
     // the oriented entries once more, ordered by the owner of the LONGER list of each intersection: the groups
     // running at any time then probe a handful of tables (L1/L2 hits) instead of thousands (DRAM sectors)
     gx::DevBuf<uint32_t> lcc_eu, lcc_ev; // om each: source, target | multiplicity bit
+    gx::DevBuf<uint32_t> lcc_owner;      // om: that owner (the sort key), ascending -- consecutive entries of one owner form a segment
 
     void *cdlp_plan = nullptr;        // gx::CdlpPlan (algo_cdlp.cu), degree bins + spill tables
     void *pr_cache = nullptr;         // gx::PrTiles (algo_pr.cu), tiling of the in-edge entries
