@@ -25,7 +25,6 @@
 
 namespace gx {
 
-constexpr int LCC_G = 8;
 constexpr uint32_t LCC_RUN = 1024; // entries a CTA draws at a time (32 trips of its 32 groups; 64 / 256 / 1024 / 4096: 85 / 77 / 74.5 / 76 ms)
 constexpr uint32_t IDMASK = ~LCC_MULT_BIT;
 
@@ -35,48 +34,61 @@ constexpr uint32_t LCC_SMEM_SLOTS = 8192; // membership tables up to this many s
 // longer row's membership table -- TAB_SMEM: the CTA's shared-memory copy of it (0.27 LSU wavefronts per probe instead
 // of one: the run's probes are ~200x the table's size), else in global memory; rows under LCC_TAB_MIN entries have no
 // table and are searched.  Adds the corner counts of the common neighbours, returns this lane's share for u and v.
-template <bool TAB_SMEM>
+template <bool TAB_SMEM, int UNROLL, int LCC_G>
 __device__ __forceinline__ void lcc_intersect(const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ tab, const uint32_t *s_tab,
                                               uint64_t sa, uint64_t sb, uint64_t la, uint64_t lb, uint64_t t0, uint64_t tmask,
                                               unsigned sub, bool u_short, unsigned long long m_uv, unsigned long long *__restrict__ num,
-                                              unsigned long long &su, unsigned long long &sv)
+                                              unsigned long long &su, unsigned long long &sv, int diag)
 {
-    for (uint64_t i = sa + sub; i < sb; i += LCC_G) {
-        const uint32_t cs = ocol[i];
-        const uint32_t w = cs & IDMASK;
-        uint32_t cl = 0xFFFFFFFFu; // the longer list's entry for w, if any
-        if (tmask) {
-            // open addressing at load 1/4: a miss ends after 1.4 probes on average, all in one line
-            uint64_t sl = lcc_tab_hash(w, tmask);
-            for (;;) {
-                const uint32_t c = TAB_SMEM ? s_tab[sl] : tab[t0 + sl];
-                if (c == 0xFFFFFFFFu || (c & IDMASK) == w) { cl = c; break; }
-                sl = (sl + 1) & (tmask - 1);
-            }
-        } else {
-            uint64_t lo = la, hi = lb;
-            while (lo < hi) {
-                const uint64_t mid = (lo + hi) >> 1;
-                if ((ocol[mid] & IDMASK) < w) lo = mid + 1; else hi = mid;
-            }
-            if (lo < lb) cl = ocol[lo];
+    // UNROLL elements of the shorter list are requested before the first one is looked up: the walk is a chain of
+    // dependent L2 / DRAM latencies otherwise (one load in flight per lane)
+    for (uint64_t i = sa + sub; i < sb; i += LCC_G * UNROLL) {
+        uint32_t cs_[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const uint64_t k = i + (uint64_t)j * LCC_G;
+            cs_[j] = k < sb ? ocol[k] : 0xFFFFFFFFu; // (no entry has this value: ids are < 2^31 - 1)
         }
-        if (cl != 0xFFFFFFFFu && (cl & IDMASK) == w) {
-            const unsigned long long m_s = (cs & LCC_MULT_BIT) ? 2ull : 1ull; // side (short owner, w)
-            const unsigned long long m_l = (cl & LCC_MULT_BIT) ? 2ull : 1ull; // side (long owner, w)
-            // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v)
-            su += u_short ? m_l : m_s;
-            sv += u_short ? m_s : m_l;
-            atomicAdd(&num[w], m_uv);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const uint32_t cs = cs_[j];
+            if (cs == 0xFFFFFFFFu) continue;
+            const uint32_t w = cs & IDMASK;
+            uint32_t cl = 0xFFFFFFFFu; // the longer list's entry for w, if any
+            if (tmask) {
+                // open addressing at load 1/4: a miss ends after 1.4 probes on average, all in one line
+                uint64_t sl = lcc_tab_hash(w, tmask);
+                for (;;) {
+                    const uint32_t c = TAB_SMEM ? s_tab[sl] : tab[t0 + sl];
+                    if (c == 0xFFFFFFFFu || (c & IDMASK) == w) { cl = c; break; }
+                    sl = (sl + 1) & (tmask - 1);
+                }
+            } else {
+                uint64_t lo = la, hi = lb;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if ((ocol[mid] & IDMASK) < w) lo = mid + 1; else hi = mid;
+                }
+                if (lo < lb) cl = ocol[lo];
+            }
+            if (cl != 0xFFFFFFFFu && (cl & IDMASK) == w) {
+                const unsigned long long m_s = (cs & LCC_MULT_BIT) ? 2ull : 1ull; // side (short owner, w)
+                const unsigned long long m_l = (cl & LCC_MULT_BIT) ? 2ull : 1ull; // side (long owner, w)
+                // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v)
+                su += u_short ? m_l : m_s;
+                sv += u_short ? m_s : m_l;
+                if (!diag) atomicAdd(&num[w], m_uv); // diag (GX_LCC_VAR=1): timing diagnostic, results are wrong
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(256, 6)
+template <int UNROLL, int LCC_G>
+__global__ void __launch_bounds__(256)
 k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ eu,
             const uint32_t *__restrict__ ev, const uint32_t *__restrict__ eowner, const uint64_t *__restrict__ tab_off,
             const uint32_t *__restrict__ tab, uint64_t e0, uint64_t om, uint32_t run, unsigned long long *__restrict__ next_run,
-            unsigned long long *__restrict__ num)
+            unsigned long long *__restrict__ num, int diag)
 {
     // oriented entries [e0, om) are this rank's share, ordered by the owner of the longer list of their intersection.
     // A CTA draws runs of `run` consecutive entries from a counter (the draw balances the load whatever a run costs) and
@@ -122,8 +134,8 @@ k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol,
                     const bool u_short = (ub - ua) <= (vb - va);
                     const uint64_t sa = u_short ? ua : va, sb = u_short ? ub : vb;
                     const uint64_t la = u_short ? va : ua, lb = u_short ? vb : ub;
-                    if (staged) lcc_intersect<true>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv);
-                    else lcc_intersect<false>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv);
+                    if (staged) lcc_intersect<true, UNROLL, LCC_G>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv, diag);
+                    else lcc_intersect<false, UNROLL, LCC_G>(ocol, tab, s_tab, sa, sb, la, lb, t0, tmask, sub, u_short, m_uv, num, su, sv, diag);
                 }
 #pragma unroll
                 for (int o = LCC_G / 2; o > 0; o >>= 1) {
@@ -173,15 +185,22 @@ extern "C" int gx_lcc(gx_graph *g, double *lcc_host)
             num.zero();
             next_run.zero();
             uint32_t run = LCC_RUN;
-            GX_CUDA(cudaFuncSetAttribute(k_lcc_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LCC_SMEM_SLOTS * sizeof(uint32_t))));
+            int unroll = 4; // elements of the shorter list in flight per lane (tuning knob: 1 / 2 / 4 / 8)
+            if (const char *e = getenv("GX_LCC_UNROLL")) unroll = atoi(e);
+            int lanes = 8; // lanes per oriented entry (tuning knob: 4 / 8 / 16)
+            if (const char *e = getenv("GX_LCC_G")) lanes = atoi(e);
+            auto kern = lanes == 4 ? (unroll <= 2 ? k_lcc_count<2, 4> : k_lcc_count<4, 4>)
+                      : lanes == 16 ? (unroll <= 2 ? k_lcc_count<2, 16> : k_lcc_count<4, 16>)
+                      : (unroll <= 1 ? k_lcc_count<1, 8> : unroll == 2 ? k_lcc_count<2, 8> : unroll <= 4 ? k_lcc_count<4, 8> : k_lcc_count<8, 8>);
+            GX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LCC_SMEM_SLOTS * sizeof(uint32_t))));
             // tuning knob; a multiple of 32 so that the four 8-lane groups of a warp make the same number of trips
             // (the shuffles inside the trip are warp-wide)
             if (const char *e = getenv("GX_LCC_RUN")) run = (uint32_t)atoi(e) >= 32 ? ((uint32_t)atoi(e) + 31u) & ~31u : 32;
             // the oriented entry list is split evenly over the ranks; corner counts are summed
             const Partition part = make_even_partition(g->om);
             if (part.hi > part.lo)
-                GX_LAUNCH(k_lcc_count, grid_persistent(6), 256, LCC_SMEM_SLOTS * sizeof(uint32_t), g->orowptr.p, g->ocol.p, g->lcc_eu.p,
-                          g->lcc_ev.p, g->lcc_owner.p, g->ltab_off.p, g->ltab.p, part.lo, part.hi, run, next_run.p, num.p);
+                GX_LAUNCH(kern, grid_persistent(6), 256, LCC_SMEM_SLOTS * sizeof(uint32_t), g->orowptr.p, g->ocol.p, g->lcc_eu.p,
+                          g->lcc_ev.p, g->lcc_owner.p, g->ltab_off.p, g->ltab.p, part.lo, part.hi, run, next_run.p, num.p, getenv("GX_LCC_VAR") ? atoi(getenv("GX_LCC_VAR")) : 0);
             allreduce(num.p, n, Dt::U64, Red::Sum);
             GX_LAUNCH(k_lcc_final, grid_persistent(8), 256, 0, num.p, g->udeg.p, n, g->res_f64.p);
         }

@@ -787,6 +787,36 @@ __global__ void k_lcc_owner_keys(const uint64_t *__restrict__ orowptr, const uin
     }
 }
 
+// first-level order inside an owner's segment: by the length of the SHORTER list, longest first -- the 8-lane groups
+// of a warp (and the warps of a CTA) then walk lists of similar length side by side instead of waiting for the longest
+__global__ void k_lcc_len_keys(const uint64_t *__restrict__ orowptr, const uint32_t *__restrict__ orow,
+                               const uint32_t *__restrict__ ocol, uint64_t om, uint32_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < om; e += stride) {
+        const uint32_t u = orow[e], v = ocol[e] & ~LCC_MULT_BIT;
+        const uint64_t du = orowptr[u + 1] - orowptr[u], dv = orowptr[v + 1] - orowptr[v];
+        const uint64_t sh = du <= dv ? du : dv;
+        key[e] = 0xFFFFu - (uint32_t)(sh > 0xFFFFull ? 0xFFFFull : sh);
+        idx[e] = (uint32_t)e;
+    }
+}
+
+// owner (the vertex whose list is the longer one) of the entries in the order idx[]
+__global__ void k_lcc_owner_of(const uint64_t *__restrict__ orowptr, const uint32_t *__restrict__ orow,
+                               const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ idx, uint64_t om, uint32_t *__restrict__ key)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < om; i += stride) {
+        const uint32_t e = idx[i];
+        const uint32_t u = orow[e], v = ocol[e] & ~LCC_MULT_BIT;
+        const uint64_t du = orowptr[u + 1] - orowptr[u], dv = orowptr[v + 1] - orowptr[v];
+        key[i] = du <= dv ? v : u;
+    }
+}
+
 __global__ void k_lcc_permute(const uint32_t *__restrict__ idx, const uint32_t *__restrict__ orow, const uint32_t *__restrict__ ocol,
                               uint64_t om, uint32_t *__restrict__ eu, uint32_t *__restrict__ ev)
 {
@@ -872,11 +902,15 @@ void ensure_lcc_cache(gx_graph *g)
         g->lcc_eu.alloc(om);
         g->lcc_ev.alloc(om);
         DevBuf<uint32_t> key(om), key_alt(om), idx(om), idx_alt(om);
-        GX_LAUNCH(k_lcc_owner_keys, grid_persistent(8), 256, 0, g->orowptr.p, g->orow.p, g->ocol.p, om, key.p, idx.p);
         cub::DoubleBuffer<uint32_t> dk(key.p, key_alt.p), dv(idx.p, idx_alt.p);
         size_t tb2 = 0;
         GX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int64_t)om, 0, bits_for(n), ctx().stream));
         DevBuf<char> tmp2(tb2);
+        // two stable sorts: by the shorter list's length (16 bits), then by owner -- inside an owner's segment the
+        // entries stay ordered by length
+        GX_LAUNCH(k_lcc_len_keys, grid_persistent(8), 256, 0, g->orowptr.p, g->orow.p, g->ocol.p, om, dk.Current(), dv.Current());
+        GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, dk, dv, (int64_t)om, 0, 16, ctx().stream));
+        GX_LAUNCH(k_lcc_owner_of, grid_persistent(8), 256, 0, g->orowptr.p, g->orow.p, g->ocol.p, dv.Current(), om, dk.Current());
         GX_CUDA(cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, dk, dv, (int64_t)om, 0, bits_for(n), ctx().stream));
         GX_LAUNCH(k_lcc_permute, grid_persistent(8), 256, 0, dv.Current(), g->orow.p, g->ocol.p, om, g->lcc_eu.p, g->lcc_ev.p);
         // the sorted keys are kept: the counting kernel finds the owner segments of a run by comparing them
