@@ -650,6 +650,20 @@ __global__ void k_sssp_m_pack(const SsspCounters *__restrict__ cnt, SsspRound *_
     r->relaxed = cnt->relaxed;
 }
 
+// the round's exchange through the peer mailboxes (comm.cuh): {queue size, ~smallest waiting distance} max-reduced
+// over the ranks, result into host-mapped memory; the counters are reset for the next round on the way
+__global__ void __launch_bounds__(32) k_sssp_m_exchange(MailTable t, SsspCounters *__restrict__ cnt, unsigned long long seq,
+                                                         unsigned long long *__restrict__ host_out)
+{
+    const unsigned long long qn = cnt->next_count, nf = ~cnt->far_min, relaxed = cnt->relaxed;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        cnt->next_count = 0; cnt->big_count = 0; cnt->relaxed = 0; cnt->far_count = 0; cnt->r_count = 0;
+        cnt->far_min = ~0ull;
+    }
+    peer_mail_exchange(t, qn, nf, relaxed, seq, host_out);
+}
+
 __global__ void k_sssp_m_out(const unsigned long long *__restrict__ dist, uint64_t v0, uint64_t v1, double *__restrict__ out)
 {
     uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,7 +702,13 @@ static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uin
         GX_CUDA(cudaStreamSynchronize(c.stream));
     }
     auto bits = [](double x) { unsigned long long b; memcpy(&b, &x, sizeof(b)); return b; };
+    // the per-round exchange: peer mailboxes (GX_SSSP_MAIL=0: NCCL all-reduce + device-to-host copy)
+    PeerMail no_mail;
+    const char *me = getenv("GX_SSSP_MAIL");
+    PeerMail &mail = (me && me[0] == '0') ? no_mail : context_mail();
     GX_LAUNCH(k_sssp_m_init, grid_persistent(8), 256, 0, dist, n, (uint32_t)src, ldone.p, hdone.p, own);
+    cnt.zero();
+    GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
     round.zero();
     allreduce(round.p, 2, Dt::U64, Red::Max); // nobody may forward into a rank's array before that rank has initialised it
     double T = delta;
@@ -696,8 +716,10 @@ static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uin
     // one round: build the queue of due vertices, expand them, exchange {queue size, smallest waiting distance};
     // the all-reduce is also the barrier after which every forwarded improvement of the round has landed
     auto run_round = [&](bool heavy, SsspRound &h) {
-        cnt.zero();
-        GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
+        if (!mail.ok) {
+            cnt.zero();
+            GX_CUDA(cudaMemsetAsync(&cnt.p->far_min, 0xFF, sizeof(unsigned long long), c.stream));
+        }
         if (heavy) {
             GX_LAUNCH(k_sssp_m_build<true>, grid_persistent(8), 256, 0, dist, hdone.p, v0, v1, bits(T), queue.p, cnt.p);
             GX_LAUNCH((k_sssp_expand<16, true>), grid_persistent(8), 256, 0, g->out.rowptr.p, g->out.col.p, g->out.w.p, queue.p,
@@ -711,9 +733,17 @@ static bool sssp_multi_delta(gx_graph *g, const SsspCache &sc, uint64_t src, uin
             GX_LAUNCH(k_sssp_relax_pieces, grid_persistent(8), 256, 0, sc.lcol.p, sc.lw.p, big_row.p, big_begin.p, big_end.p, dist, nullptr,
                       cnt.p, bits(T), -1.0, peers.p);
         }
-        GX_LAUNCH(k_sssp_m_pack, 1, 1, 0, cnt.p, round.p);
-        allreduce(round.p, 2, Dt::U64, Red::Max);
-        read_back(&h, round.p, sizeof(h));
+        if (mail.ok) {
+            const unsigned long long seq = ++mail.seq;
+            GX_LAUNCH(k_sssp_m_exchange, 1, 32, 0, mail.table, cnt.p, seq, mail.host_dev);
+            unsigned long long out[3];
+            peer_mail_wait(mail, seq, out);
+            h.qn = out[0]; h.neg_far_min = out[1]; h.relaxed = out[2];
+        } else {
+            GX_LAUNCH(k_sssp_m_pack, 1, 1, 0, cnt.p, round.p);
+            allreduce(round.p, 2, Dt::U64, Red::Max);
+            read_back(&h, round.p, sizeof(h));
+        }
         relaxed += h.relaxed;
         rounds++;
     };

@@ -1,6 +1,8 @@
 // comm.cu -- NCCL collectives on the library stream (see comm.cuh for the sharding model).
 #include <nccl.h>
 
+#include <chrono>
+#include <cstring>
 #include <vector>
 
 #include "comm.cuh"
@@ -83,8 +85,25 @@ static void peer_release(PeerBuf &b)
     b = PeerBuf{};
 }
 
+static PeerMail g_mail;
+static bool g_mail_tried = false;
+
+PeerMail &context_mail()
+{
+    if (!g_mail_tried) {
+        g_mail_tried = true;
+        peer_mail_open(g_mail);
+    }
+    return g_mail;
+}
+
 void peer_cache_clear()
 {
+    if (g_mail_tried) {
+        if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+        peer_mail_close(g_mail);
+        g_mail_tried = false;
+    }
     if (g_parked.empty()) return;
     if (ctx().ready) cudaStreamSynchronize(ctx().stream);
     for (PeerBuf &p : g_parked) peer_release(p);
@@ -151,6 +170,59 @@ void peer_free(PeerBuf &b)
     }
     if (c.ready) cudaStreamSynchronize(c.stream);
     peer_release(b);
+}
+
+void peer_mail_open(PeerMail &m)
+{
+    Context &c = ctx();
+    m = PeerMail{};
+    peer_alloc(m.buf, (size_t)2 * MAX_PEERS * MAIL_WORDS * sizeof(unsigned long long));
+    if (!m.buf.shared) { peer_free(m.buf); return; }
+    GX_CUDA(cudaMemsetAsync(m.buf.local, 0, m.buf.bytes, c.stream));
+    for (int r = 0; r < c.nranks; r++) m.table.peer[r] = (unsigned long long *)m.buf.peer[r];
+    m.table.nranks = c.nranks;
+    m.table.rank = c.rank;
+    GX_CUDA(cudaHostAlloc((void **)&m.host, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(m.host, 0, 8 * sizeof(unsigned long long));
+    GX_CUDA(cudaHostGetDevicePointer((void **)&m.host_dev, m.host, 0));
+    // nobody may store into a mailbox before its owner has cleared it
+    DevBuf<int> flag(1);
+    flag.zero();
+    allreduce(flag.p, 1, Dt::I32, Red::Max);
+    GX_CUDA(cudaStreamSynchronize(c.stream));
+    m.seq = 0;
+    m.ok = true;
+}
+
+void peer_mail_close(PeerMail &m)
+{
+    if (m.host) cudaFreeHost(m.host);
+    m.host = m.host_dev = nullptr;
+    if (m.buf.local) peer_free(m.buf);
+    m.ok = false;
+}
+
+void peer_mail_wait(PeerMail &m, unsigned long long seq, unsigned long long out[3])
+{
+    volatile unsigned long long *h = m.host + (size_t)(seq & 1ull) * 4;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    for (;;) {
+        const unsigned long long s = h[3];
+        if (s == seq) break;
+        if (s == ~0ull) throw Error(GX_ERR_CUDA, "peer mailbox exchange timed out on the device (a rank stopped responding)");
+        if ((++spins & 0xFFFFu) == 0) {
+            if (cudaStreamQuery(ctx().stream) != cudaErrorNotReady && h[3] != seq) {
+                GX_CUDA(cudaGetLastError());
+                if (h[3] == seq) break;
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+                throw Error(GX_ERR_CUDA, "peer mailbox exchange timed out on the host");
+        }
+    }
+    out[0] = h[0];
+    out[1] = h[1];
+    out[2] = h[2];
 }
 
 static ncclDataType_t nccl_dt(Dt dt)

@@ -40,6 +40,77 @@ void peer_alloc(PeerBuf &b, size_t bytes);
 void peer_free(PeerBuf &b);
 void peer_cache_clear(); // releases the buffers parked for reuse (before the communicator goes away)
 
+// Latency-critical tiny exchanges (a queue size and a minimum per round of a frontier algorithm) go through
+// peer-mapped MAILBOXES instead of NCCL + a device-to-host copy: a rank stores its words into slot [rank] of every
+// peer's mailbox over NVLink, spins until all slots of its own mailbox carry the round's sequence number, and
+// leaves the reduced result in host-mapped memory where the host polls it.  Like an all-reduce it is also a barrier:
+// a rank's words are stored after its earlier kernels on the stream have completed.  Two slot sets alternate by the
+// parity of the sequence number (a rank can run at most one exchange ahead of a peer).
+constexpr int MAIL_WORDS = 4; // a, b, sequence number, (pad)
+struct MailTable {
+    unsigned long long *peer[MAX_PEERS]; // rank r's mailbox as seen from here
+    int nranks, rank;
+};
+struct PeerMail {
+    PeerBuf buf;                          // 2 * MAX_PEERS * MAIL_WORDS words
+    MailTable table{};
+    unsigned long long *host = nullptr;   // pinned, mapped: [parity][4] = max a, max b, local extra, sequence number
+    unsigned long long *host_dev = nullptr;
+    unsigned long long seq = 0;
+    bool ok = false;
+};
+void peer_mail_open(PeerMail &m);   // collective; m.ok = false when the peer mapping is unavailable
+void peer_mail_close(PeerMail &m);
+// the communicator's own mailbox: opened by the first caller (collective: all ranks reach it in the same call),
+// reused by every later exchange (sequence numbers keep counting), closed with the communicator
+PeerMail &context_mail();
+// waits (host side) for the result of the exchange with sequence number `seq`: out = {max a, max b, extra}
+void peer_mail_wait(PeerMail &m, unsigned long long seq, unsigned long long out[3]);
+
+#ifdef __CUDACC__
+// one warp (threadIdx.x < 32 of one CTA); returns on every lane; the result goes to host memory
+__device__ __forceinline__ void peer_mail_exchange(const MailTable &t, unsigned long long a, unsigned long long b,
+                                                   unsigned long long extra, unsigned long long seq,
+                                                   unsigned long long *__restrict__ host_out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned par = (unsigned)(seq & 1ull);
+    if ((int)lane < t.nranks) {
+        volatile unsigned long long *slot = t.peer[lane] + ((size_t)par * MAX_PEERS + t.rank) * MAIL_WORDS;
+        slot[0] = a;
+        slot[1] = b;
+        __threadfence_system();
+        slot[2] = seq;
+    }
+    unsigned long long ma = 0, mb = 0;
+    bool bad = false;
+    if ((int)lane < t.nranks) {
+        volatile unsigned long long *mine = t.peer[t.rank] + ((size_t)par * MAX_PEERS + lane) * MAIL_WORDS;
+        const long long t0 = clock64();
+        while (mine[2] != seq)
+            if (clock64() - t0 > 8000000000ll) { bad = true; break; } // ~4 s: a peer died; the host raises an error
+        __threadfence_system();
+        ma = mine[0];
+        mb = mine[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long xa = __shfl_xor_sync(0xffffffffu, ma, o), xb = __shfl_xor_sync(0xffffffffu, mb, o);
+        ma = xa > ma ? xa : ma;
+        mb = xb > mb ? xb : mb;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        volatile unsigned long long *h = host_out + (size_t)par * 4;
+        h[0] = ma;
+        h[1] = mb;
+        h[2] = extra;
+        __threadfence_system();
+        h[3] = bad ? ~0ull : seq;
+    }
+}
+#endif
+
 enum class Red { Sum, Min, Max };
 enum class Dt { U32, I32, U64, F64, U8 };
 
