@@ -12,7 +12,13 @@
 //        on the first parent in the frontier bitmap; one warp owns one
 //        32-vertex bitmap word, written with a ballot (no atomics); rows longer
 //        than ROW_SPLIT go to a warp-per-row kernel
+// One GPU: the whole search is ONE cooperative launch (k_bfs_run): the level loop, the direction rule and the
+// frontier bookkeeping run on the device with grid-wide barriers between the phases of a level, so a level costs a
+// few barriers (~2 us each) instead of 3-4 launches, a memset and a device-to-host read of the counters.  Several
+// GPUs keep the host loop (every pull level ends in an all-gather of the next frontier's bitmap words).
 // Algorithmic bytes (one-pass bound): 4 m_reach + 8(n+1) + 4n + 2 (n/8) levels.
+#include <cooperative_groups.h>
+
 #include "graph.cuh"
 
 namespace gx {
@@ -46,10 +52,10 @@ __device__ __forceinline__ void bfs_append(bool won, uint32_t v, uint32_t *next_
     if (won) next_q[base + __popc(mask & ((1u << lane_id()) - 1u))] = v;
 }
 
-__global__ void __launch_bounds__(256)
-k_bfs_push(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ queue,
-           uint64_t qn, int32_t *__restrict__ level, int32_t depth, uint32_t *__restrict__ next_q,
-           uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, BfsCounters *__restrict__ cnt)
+__device__ __forceinline__ void
+bfs_push_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ queue,
+               uint64_t qn, int32_t *__restrict__ level, int32_t depth, uint32_t *__restrict__ next_q,
+               uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, BfsCounters *__restrict__ cnt)
 {
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -83,9 +89,17 @@ k_bfs_push(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col
 }
 
 __global__ void __launch_bounds__(256)
-k_bfs_push_big(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ big_row,
-               const uint64_t *__restrict__ big_begin, int32_t *__restrict__ level, int32_t depth,
-               uint32_t *__restrict__ next_q, BfsCounters *__restrict__ cnt)
+k_bfs_push(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ queue,
+           uint64_t qn, int32_t *__restrict__ level, int32_t depth, uint32_t *__restrict__ next_q,
+           uint32_t *__restrict__ big_row, uint64_t *__restrict__ big_begin, BfsCounters *__restrict__ cnt)
+{
+    bfs_push_phase(rowptr, col, queue, qn, level, depth, next_q, big_row, big_begin, cnt);
+}
+
+__device__ __forceinline__ void
+bfs_push_big_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ big_row,
+                   const uint64_t *__restrict__ big_begin, int32_t *__restrict__ level, int32_t depth,
+                   uint32_t *__restrict__ next_q, BfsCounters *__restrict__ cnt)
 {
     const unsigned long long nbig = cnt->big_count;
     unsigned long long nf = 0, mf = 0;
@@ -110,9 +124,17 @@ k_bfs_push_big(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__
     if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
 }
 
+__global__ void __launch_bounds__(256)
+k_bfs_push_big(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ big_row,
+               const uint64_t *__restrict__ big_begin, int32_t *__restrict__ level, int32_t depth,
+               uint32_t *__restrict__ next_q, BfsCounters *__restrict__ cnt)
+{
+    bfs_push_big_phase(rowptr, col, big_row, big_begin, level, depth, next_q, cnt);
+}
+
 // frontier (level == cur) and visited (level != UNVIS) bitmaps from the level array
-__global__ void k_bfs_bitmaps(const int32_t *__restrict__ level, uint64_t n, int32_t cur, uint32_t *__restrict__ front,
-                              uint32_t *__restrict__ visited)
+__device__ __forceinline__ void bfs_bitmaps_phase(const int32_t *__restrict__ level, uint64_t n, int32_t cur,
+                                                  uint32_t *__restrict__ front, uint32_t *__restrict__ visited)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -125,11 +147,17 @@ __global__ void k_bfs_bitmaps(const int32_t *__restrict__ level, uint64_t n, int
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_bfs_pull(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
-           const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1,
-           const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
-           int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
+__global__ void k_bfs_bitmaps(const int32_t *__restrict__ level, uint64_t n, int32_t cur, uint32_t *__restrict__ front,
+                              uint32_t *__restrict__ visited)
+{
+    bfs_bitmaps_phase(level, n, cur, front, visited);
+}
+
+__device__ __forceinline__ void
+bfs_pull_phase(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+               const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1,
+               const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+               int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
 {
     // [v0, v1) is this rank's row block; v0 is a multiple of 32, so a warp still owns whole words
     uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,12 +187,21 @@ k_bfs_pull(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ 
     if (lane_id() == 0 && (nf | scanned)) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); atomicAdd(&cnt->next_count, scanned); }
 }
 
-// rows the thread-per-vertex kernel skipped: one warp per long row, ballot early exit
 __global__ void __launch_bounds__(256)
-k_bfs_pull_long(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
-                const uint64_t *__restrict__ out_rowptr, const uint32_t *__restrict__ long_rows, uint64_t n_long,
-                const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
-                int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
+k_bfs_pull(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+           const uint64_t *__restrict__ out_rowptr, uint64_t n, uint64_t v0, uint64_t v1,
+           const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+           int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
+{
+    bfs_pull_phase(in_rowptr, in_col, out_rowptr, n, v0, v1, front, visited, next, level, depth, cnt);
+}
+
+// rows the thread-per-vertex kernel skipped: one warp per long row, ballot early exit
+__device__ __forceinline__ void
+bfs_pull_long_phase(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+                    const uint64_t *__restrict__ out_rowptr, const uint32_t *__restrict__ long_rows, uint64_t n_long,
+                    const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+                    int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
 {
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -192,6 +229,15 @@ k_bfs_pull_long(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restri
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_bfs_pull_long(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restrict__ in_col,
+                const uint64_t *__restrict__ out_rowptr, const uint32_t *__restrict__ long_rows, uint64_t n_long,
+                const uint32_t *__restrict__ front, uint32_t *__restrict__ visited, uint32_t *__restrict__ next,
+                int32_t *__restrict__ level, int32_t depth, BfsCounters *__restrict__ cnt)
+{
+    bfs_pull_long_phase(in_rowptr, in_col, out_rowptr, long_rows, n_long, front, visited, next, level, depth, cnt);
 }
 
 // Multi-GPU pull: after the owners' bitmap words were all-gathered, every rank applies the words

@@ -144,18 +144,23 @@ __device__ __forceinline__ void w_store(double *__restrict__ own, const WOut *__
 // 16-byte loads and stores over NVLink (one launch, no protocol, full-width stores -- unlike the 8-byte
 // scattered stores of the fused path).  Peer p is served by the CTAs with blockIdx.x % npeer == p, so all
 // links are busy at once.  The all-reduce of the sink mass that opens the next iteration is the barrier.
+// A rank's segment has two pieces (often-gathered slots | the rest, see PrTiles); both counts are multiples of 32.
 __global__ void __launch_bounds__(256)
-k_pr_push_segment(const double *__restrict__ own, const WOut *__restrict__ o, uint64_t first, uint64_t count)
+k_pr_push_segment(const double *__restrict__ own, const WOut *__restrict__ o, uint64_t first, uint64_t count,
+                  uint64_t first2, uint64_t count2)
 {
     const int npeer = o->npeer;
     if (npeer == 0) return;
     const int p = blockIdx.x % npeer;
     const unsigned rank_in_peer = blockIdx.x / npeer, ctas_per_peer = gridDim.x / npeer; // gridDim.x is a multiple of npeer
-    const double2 *src = (const double2 *)(own + first); // segments start at multiples of 32 slots: 16-byte aligned
+    const uint64_t n2 = count / 2, m2 = count2 / 2;
+    const double2 *src = (const double2 *)(own + first); // pieces start at multiples of 32 slots: 16-byte aligned
     double2 *dst = (double2 *)(o->peer[p] + first);
-    const uint64_t n2 = count / 2;
-    for (uint64_t i = (uint64_t)rank_in_peer * 256 + threadIdx.x; i < n2; i += (uint64_t)ctas_per_peer * 256) dst[i] = src[i];
-    if (rank_in_peer == 0 && threadIdx.x == 0 && (count & 1)) o->peer[p][first + count - 1] = own[first + count - 1];
+    const double2 *srcb = (const double2 *)(own + first2);
+    double2 *dstb = (double2 *)(o->peer[p] + first2);
+    for (uint64_t i = (uint64_t)rank_in_peer * 256 + threadIdx.x; i < n2 + m2; i += (uint64_t)ctas_per_peer * 256) {
+        if (i < n2) dst[i] = src[i]; else dstb[i - n2] = srcb[i - n2];
+    }
 }
 
 __global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
@@ -169,6 +174,8 @@ __global__ void k_fill_f64(double *__restrict__ p, uint64_t n, double v)
 constexpr int PT_TILE = 256;
 constexpr int PT_WARPS = 32;          // one 1024-thread CTA per SM (64 registers per thread)
 constexpr uint32_t PT_HOT = 24576;    // hottest entries of w staged in shared memory (192 KB)
+constexpr uint64_t PT_WARM_MB = 48;   // often-gathered slots kept in L2 when w does not fit (all ranks' warm pieces together)
+constexpr uint64_t PT_HINT_MIN_MB = 56; // w smaller than this stays in L2 by itself: one load policy
 
 struct PrTiles {
     uint64_t K = 0, M = 0, n_tiles = 0, n_span = 0, n_empty = 0; // non-empty rows, entries, ...
@@ -176,6 +183,12 @@ struct PrTiles {
     DevBuf<uint64_t> ne_ptr;    // K+1: local entry offset of its first entry (ne_ptr[0] = 0, ne_ptr[K] = M)
     DevBuf<uint32_t> pi;        // n: vertex -> slot in the index space w lives in (see k_pt_make_pi)
     uint64_t seg = 0, slots = 0; // slots per rank segment (equal, padded), nranks * seg
+    // A segment is stored in two pieces so that the often-gathered slots of ALL ranks are one address range:
+    // [rank 0 | rank 1 | ...] x wps slots (each rank's highest out-degrees), then [rank 0 | rank 1 | ...] x tps slots
+    // (the rest); seg = wps + tps.  Gathers below `warm_end` ask L2 to keep their lines (evict_last), the tail is
+    // read evict_first: on RMAT-25 w is 136 MB -- larger than L2 -- and its first third takes 90 % of the gathers.
+    uint64_t wps = 0, tps = 0;
+    bool hint = false;           // the two-policy gather is compiled in (w larger than about half of L2)
     uint32_t hps = 0, hot = 0;   // hot entries per segment / in total (hps * nranks): the stored ids are h < hot for the
                                  // hottest hps slots of every segment and slot + hot for all others
     PeerBuf wbuf[2];             // the two copies of w (read / written in turn), mapped into all ranks
@@ -237,13 +250,14 @@ __global__ void k_pt_degree_keys(const uint64_t *__restrict__ out_rowptr, uint64
 // slot of the i-th vertex in sorted order: rank r's vertices fill the first (b[r+1] - b[r]) slots of the
 // segment [r * seg, (r+1) * seg) -- equal, padded segments, so the exchange is one plain all-gather
 __global__ void k_pt_make_pi(const uint32_t *__restrict__ sorted_keys, const uint32_t *__restrict__ sorted_vertex, uint64_t n,
-                             const uint64_t *__restrict__ bounds, uint64_t seg, uint32_t *__restrict__ pi)
+                             const uint64_t *__restrict__ bounds, uint64_t wps, uint64_t tps, uint64_t nranks,
+                             uint32_t *__restrict__ pi)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const uint64_t owner = sorted_keys[i] >> 24;
-        pi[sorted_vertex[i]] = (uint32_t)(owner * seg + (i - bounds[owner]));
+        const uint64_t owner = sorted_keys[i] >> 24, off = i - bounds[owner];
+        pi[sorted_vertex[i]] = (uint32_t)(off < wps ? owner * wps + off : nranks * wps + owner * tps + (off - wps));
     }
 }
 
@@ -252,16 +266,20 @@ __global__ void k_pt_make_pi(const uint32_t *__restrict__ sorted_keys, const uin
 // so the kernel's test stays one compare.  Entries beyond `count` pad the last tile: they gather the
 // always-zero slot `zero_slot`.
 __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pi, uint64_t count,
-                                   uint64_t padded, uint32_t zero_slot, uint32_t seg, uint32_t hps, uint32_t hot,
-                                   uint32_t *__restrict__ out)
+                                   uint64_t padded, uint32_t zero_slot, uint32_t wps, uint32_t warm_slots, uint32_t hps,
+                                   uint32_t hot, uint32_t *__restrict__ out)
 {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (; e < padded; e += stride) {
         uint32_t slot = zero_slot;
         if (e < count) slot = pi[col[e]];
-        const uint32_t owner = slot < seg ? 0u : slot / seg, off = slot - owner * seg; // (one GPU: no division)
-        out[e] = (slot != zero_slot && off < hps) ? owner * hps + off : slot + hot;
+        uint32_t id = slot + hot;
+        if (slot < warm_slots) { // the hot stage holds the first hps slots of every rank's warm piece
+            const uint32_t owner = slot < wps ? 0u : slot / wps, off = slot - owner * wps; // (one GPU: no division)
+            if (off < hps) id = owner * hps + off;
+        }
+        out[e] = id;
     }
 }
 
@@ -374,7 +392,8 @@ struct PtArgs {
     const double *d_k;
     const double *w;        // degree-sorted space
     const double *w_cold;   // w - hot: stored ids >= hot are slot + hot
-    uint32_t hps, seg;      // hot entries per rank segment, segment length
+    uint32_t hps, wps;      // hot entries per rank segment, slots of a rank's warm piece (PrTiles)
+    uint32_t warm_end;      // stored ids in [hot, warm_end) ask L2 to keep their lines, the rest are read evict-first
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
     double *tele_out;
@@ -460,20 +479,40 @@ __device__ __forceinline__ void pt_tile_rows(const PtArgs &a, uint64_t t, unsign
     }
 }
 
-// the 8 gathers of a lane: hottest sources from shared memory, the rest through L1/L2
-template <int VAR>
-__device__ __forceinline__ void pt_gather8(const PtArgs &a, const double *s_hot, const uint32_t (&idx)[8], double (&val)[8])
+__device__ __forceinline__ double ld_gather_policy(const double *p, uint64_t policy)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// the 8 gathers of a lane: hottest sources from shared memory, the rest through L1/L2.  HINT (w larger than about
+// half of L2): the warm range is read with an evict-last policy, the rarely gathered tail evict-first, so that the
+// tail's lines (most of the vector, a tenth of the gathers) do not push the warm ones out of L2.
+template <int VAR, bool HINT>
+__device__ __forceinline__ void pt_gather8(const PtArgs &a, const double *s_hot, const uint32_t (&idx)[8], double (&val)[8],
+                                           uint64_t pol_keep, uint64_t pol_stream)
 {
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        val[i] = (VAR & 4) ? (double)idx[i] : (idx[i] < a.hot ? s_hot[idx[i]] : __ldg(a.w_cold + idx[i]));
+    for (int i = 0; i < 8; i++) {
+        if (VAR & 4) val[i] = (double)idx[i];
+        else if (idx[i] < a.hot) val[i] = s_hot[idx[i]];
+        else if (!HINT) val[i] = __ldg(a.w_cold + idx[i]);
+        else if (idx[i] < a.warm_end) val[i] = ld_gather_policy(a.w_cold + idx[i], pol_keep);
+        else val[i] = ld_gather_policy(a.w_cold + idx[i], pol_stream);
+    }
 }
 
 // VAR (GX_PR_VAR): 2 and 4 are TIMING DIAGNOSTICS that break the result (tools/pr_ab.py): 2 = epilogue
 // operands not loaded, 4 = no gathers -- what each dependent memory phase of a tile costs.
-template <int VAR, bool PEERS>
+template <int VAR, bool PEERS, bool HINT>
 __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
 {
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (HINT) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    }
     extern __shared__ double s_hot[];
     __shared__ double s_red[PT_WARPS + 1];
     // teleport' = (1-damping)/n + damping * sum_{sinks} r / n; every CTA adds the partials in the same order
@@ -482,7 +521,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
     // the hottest sources (highest out-degree) are read from shared memory instead of through L1/L2
     for (uint32_t h = threadIdx.x; h < a.hot; h += PT_WARPS * 32) {
         const uint32_t owner = h / a.hps;
-        s_hot[h] = a.w[(uint64_t)owner * a.seg + (h - owner * a.hps)]; // one GPU: w[h]
+        s_hot[h] = a.w[(uint64_t)owner * a.wps + (h - owner * a.hps)]; // one GPU: w[h]
     }
     __syncthreads();
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
@@ -496,7 +535,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
         uint32_t idx[8];
         ld_stream8(a.col + t * PT_TILE + 8u * lane, idx); // tiles are whole (padded) and 1 KB apart: 32-byte aligned
         double val[8];
-        pt_gather8<VAR>(a, s_hot, idx, val); // 8 independent gathers per lane
+        pt_gather8<VAR, HINT>(a, s_hot, idx, val, pol_keep, pol_stream); // 8 independent gathers per lane
         pt_tile_rows<VAR, PEERS>(a, t, lane, kk, kk_next, flags, val, tele, sink);
     }
     // rows without entries: r = teleport'; a thread each, spread over all warps of the grid (the tail of
@@ -652,14 +691,26 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         }
         uint64_t seg = 0;
         for (int r = 0; r < ctx().nranks; r++) seg = std::max<uint64_t>(seg, in.plan.part.b[r + 1] - in.plan.part.b[r]);
-        pt->seg = (seg + 31) & ~31ull;
-        pt->slots = pt->seg * (uint64_t)ctx().nranks;
+        seg = (seg + 31) & ~31ull;
         uint32_t hot_cap = PT_HOT;
         if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
-        pt->hps = (uint32_t)std::min<uint64_t>(pt->seg, hot_cap / (uint32_t)ctx().nranks);
+        pt->hps = (uint32_t)std::min<uint64_t>(seg, hot_cap / (uint32_t)ctx().nranks);
         pt->hot = pt->hps * (uint32_t)ctx().nranks;
+        // warm piece: the often-gathered head of every segment, PR_WARM_MB in total (GX_PR_WARM_MB; 0 = one piece)
+        uint64_t warm_mb = PT_WARM_MB;
+        if (const char *e = getenv("GX_PR_WARM_MB")) warm_mb = (uint64_t)atoll(e);
+        uint64_t wps = ((warm_mb << 20) / sizeof(double) / (uint64_t)ctx().nranks) & ~31ull;
+        wps = std::max<uint64_t>(wps, (pt->hps + 31u) & ~31u);
+        if (warm_mb == 0 || wps >= seg) wps = seg;
+        pt->wps = wps;
+        pt->tps = seg - wps;
+        pt->seg = seg;
+        pt->slots = pt->seg * (uint64_t)ctx().nranks;
+        pt->hint = pt->tps > 0 && pt->slots * sizeof(double) > (PT_HINT_MIN_MB << 20);
+        if (const char *e = getenv("GX_PR_HINT")) pt->hint = e[0] != '0';
         GX_REQUIRE(pt->slots + pt->hot < 0xFFFFFFFEull, "vertex slot space exceeds 32 bits");
-        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->seg, pt->pi.p);
+        GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->wps, pt->tps,
+                  (uint64_t)ctx().nranks, pt->pi.p);
     }
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
     // (padded to whole tiles with the index of a slot that always holds 0: the kernel needs no bounds checks)
@@ -667,7 +718,7 @@ static PrTiles *build_pr_tiles(gx_graph *g)
     pt->col.alloc(padded ? padded : 1);
     if (pt->M)
         GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, padded, (uint32_t)pt->slots,
-                  (uint32_t)pt->seg, pt->hps, pt->hot, pt->col.p);
+                  (uint32_t)pt->wps, (uint32_t)(pt->wps * (uint64_t)ctx().nranks), pt->hps, pt->hot, pt->col.p);
     pt->tile_k0.alloc(pt->n_tiles ? pt->n_tiles : 1);
     if (pt->n_tiles)
         GX_LAUNCH(k_pt_tile_k0, grid_for(pt->n_tiles, 256), 256, 0, pt->ne_ptr.p, pt->K, pt->n_tiles, pt->tile_k0.p);
@@ -708,9 +759,11 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     const uint32_t hot = pt.hot;
     const size_t smem = (size_t)hot * sizeof(double);
     using TilesFn = void (*)(const PtArgs);
-    static const TilesFn tiles_tab[3][2] = {{k_pr_tiles<0, false>, k_pr_tiles<0, true>}, {k_pr_tiles<2, false>, k_pr_tiles<2, true>},
-                                            {k_pr_tiles<4, false>, k_pr_tiles<4, true>}};
-    const int vi = var == 2 ? 1 : var == 4 ? 2 : 0;
+    static const TilesFn tiles_tab[4][2] = {{k_pr_tiles<0, false, false>, k_pr_tiles<0, true, false>},
+                                            {k_pr_tiles<2, false, false>, k_pr_tiles<2, true, false>},
+                                            {k_pr_tiles<4, false, false>, k_pr_tiles<4, true, false>},
+                                            {k_pr_tiles<0, false, true>, k_pr_tiles<0, true, true>}};
+    const int vi = var == 2 ? 1 : var == 4 ? 2 : pt.hint ? 3 : 0;
     const unsigned tile_threads = PT_WARPS * 32;
     TilesFn tiles_fn[2] = {tiles_tab[vi][0], tiles_tab[vi][1]};
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -790,7 +843,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         a.mask = (const uint8_t *)pt.mask.p; a.slot_k = pt.slot_k.p; a.d_k = d_k.p;
         double *w_old = wv[cur], *w_new = wv[cur ^ 1];
         const WOut *wout = peer_tab.p + (cur ^ 1);
-        a.w = w_old; a.w_cold = w_old - hot; a.hps = pt.hps ? pt.hps : 1; a.seg = (uint32_t)pt.seg; a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
+        a.w = w_old; a.w_cold = w_old - hot; a.hps = pt.hps ? pt.hps : 1; a.wps = (uint32_t)pt.wps;
+        a.warm_end = hot + (uint32_t)(pt.wps * (uint64_t)c.nranks); a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
         a.w_new.n = 1;
         a.w_new.p[0] = w_new;
         if (fused) {
@@ -821,10 +875,11 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         if (it + 1 < iters) {
             if (push) {
                 const unsigned np = (unsigned)c.nranks - 1;
-                GX_LAUNCH(k_pr_push_segment, np * ((2 * (unsigned)c.num_sms + np - 1) / np), 256, 0, w_new, wout, (uint64_t)c.rank * pt.seg,
-                          pt.seg);
+                GX_LAUNCH(k_pr_push_segment, np * ((2 * (unsigned)c.num_sms + np - 1) / np), 256, 0, w_new, wout,
+                          (uint64_t)c.rank * pt.wps, pt.wps, (uint64_t)c.nranks * pt.wps + (uint64_t)c.rank * pt.tps, pt.tps);
             } else if (!fused) {
-                allgather_equal(w_new, Dt::F64, pt.seg);
+                allgather_equal(w_new, Dt::F64, pt.wps);
+                if (pt.tps) allgather_equal(w_new + (uint64_t)c.nranks * pt.wps, Dt::F64, pt.tps);
             }
         }
         else allgatherv(rank, Dt::F64, plan.part);

@@ -32,6 +32,28 @@ __global__ void __launch_bounds__(1024, 1) k_ldg(const double *w, uint32_t wmask
     if (s == 1.2345) *out = s;
 }
 
+// texture path: tex1Dfetch<int2> on a linear texture over the same vector (TEX_PER of every 8 gathers per lane through
+// the texture unit, the others LDG): does the texture pipe have a tag rate of its own?
+template <int TEX_PER>
+__global__ void __launch_bounds__(1024, 1) k_tex(cudaTextureObject_t tex, const double *w, uint32_t wmask, int per_thread, double *out)
+{
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+    double s = 0;
+    for (int i = 0; i < per_thread; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            h = mix(h + (uint32_t)(i + j));
+            const uint32_t idx = h & wmask;
+            if (j < TEX_PER) { const int2 t = tex1Dfetch<int2>(tex, (int)idx); v[j] = __hiloint2double(t.y, t.x); }
+            else v[j] = w[idx];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += v[j];
+    }
+    if (s == 1.2345) *out = s;
+}
+
 // bulk-copy gathers: every lane issues BATCH 16-byte cp.async.bulk copies into its own staging slots, the warp waits
 // on its mbarrier, lanes read their values back from shared memory.  LSU_PER: additional LDG gathers per batch (mixed)
 template <int BATCH, int LSU_PER>
@@ -160,6 +182,17 @@ int main()
     BULK(4, 4, 8, "mixed: bulk batch 4 + 4 LDG per lane");
     BULK(2, 6, 8, "mixed: bulk batch 2 + 6 LDG per lane");
     BULK(1, 7, 8, "mixed: bulk batch 1 + 7 LDG per lane");
+    {
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = w;
+        rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = (size_t)wn * 8;
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex; CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        rep("tex1Dfetch<int2>, all 8 gathers per lane", timeit([&] { k_tex<8><<<sms, 1024>>>(tex, w, wn - 1, per_thread, outd); }), g);
+        rep("mixed: 4 tex1Dfetch + 4 LDG per lane", timeit([&] { k_tex<4><<<sms, 1024>>>(tex, w, wn - 1, per_thread, outd); }), g);
+        rep("mixed: 2 tex1Dfetch + 6 LDG per lane", timeit([&] { k_tex<2><<<sms, 1024>>>(tex, w, wn - 1, per_thread, outd); }), g);
+        CK(cudaDeviceSynchronize());
+        CK(cudaDestroyTextureObject(tex));
+    }
     CK(cudaDeviceSynchronize());
     run_dsmem<1>(w, outd, sms);
     run_dsmem<2>(w, outd, sms);
