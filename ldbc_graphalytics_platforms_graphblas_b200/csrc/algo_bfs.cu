@@ -107,7 +107,7 @@ bfs_push_big_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restri
         const uint64_t b0 = big_begin[c];
         const uint64_t row_end = rowptr[big_row[c] + 1];
         const uint64_t e_end = (b0 + CHUNK < row_end) ? b0 + CHUNK : row_end;
-        for (uint64_t base = b0; base < e_end; base += 256) {
+        for (uint64_t base = b0; base < e_end; base += blockDim.x) {
             const uint64_t e = base + threadIdx.x;
             bool won = false;
             uint32_t v = 0;
@@ -170,10 +170,26 @@ bfs_pull_phase(const uint64_t *__restrict__ in_rowptr, const uint32_t *__restric
         if (vis != 0xFFFFFFFFu && !((vis >> lane_id()) & 1u) && v < n) {
             const uint64_t a = in_rowptr[v], b = in_rowptr[v + 1];
             if (b - a <= ROW_SPLIT) {
-                for (uint64_t e = a; e < b; e++) {
-                    const uint32_t u = in_col[e];
+                // the first entry alone (in the dense levels it is a parent more often than not), then four entries and
+                // their frontier words in flight per trip: the walk is a chain of dependent loads otherwise.
+                // `scanned` counts up to the first parent, as a one-at-a-time walk would
+                if (a < b) {
+                    const uint32_t u0 = in_col[a];
                     scanned++;
-                    if ((front[u >> 5] >> (u & 31u)) & 1u) { found = true; break; }
+                    found = (front[u0 >> 5] >> (u0 & 31u)) & 1u;
+                }
+                for (uint64_t e = a + 1; e < b && !found; e += 4) {
+                    uint32_t u[4], fw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) u[j] = e + j < b ? in_col[e + j] : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) fw[j] = u[j] != 0xFFFFFFFFu ? front[u[j] >> 5] : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (found || u[j] == 0xFFFFFFFFu) continue;
+                        scanned++;
+                        if ((fw[j] >> (u[j] & 31u)) & 1u) found = true;
+                    }
                 }
             }
             if (found) { level[v] = depth; nf++; mf += out_rowptr[v + 1] - out_rowptr[v]; }
@@ -289,6 +305,100 @@ __global__ void k_bfs_widen(const int32_t *__restrict__ level, uint64_t n, int64
     for (; v < n; v += stride) { int32_t l = level[v]; out[v] = l == UNVIS ? GX_UNREACHED_LEVEL : (int64_t)l; }
 }
 
+
+// ----------------------------------------------------------------------------- one GPU: the whole search in one launch
+struct BfsRunArgs {
+    const uint64_t *out_rowptr; const uint32_t *out_col;
+    const uint64_t *in_rowptr; const uint32_t *in_col;
+    const uint32_t *long_rows; uint64_t n_long;
+    uint64_t n, m; uint32_t src; int can_pull;
+    int32_t *level; uint32_t *q0, *q1, *bm_front, *bm_next, *bm_vis;
+    uint32_t *big_row; uint64_t *big_begin;
+    BfsCounters *cnt;          // 3 slots used in turn (level d uses slot d % 3, zeroes slot (d + 1) % 3)
+    unsigned long long *qcur;  // append cursor of the pull -> push conversion
+    int64_t *out;              // widened levels
+    unsigned long long *stats; // levels, edges inspected, m_reach
+};
+
+// Same level loop, direction rule and phases as the host loop of gx_bfs below (several GPUs); every thread keeps the
+// loop state in registers -- it is a function of the counters all threads read after the same barrier.
+// CTAS: co-resident CTAs per SM the launch bound asks for (4 / 6 / 8 -> 64 / 40 / 32 registers; the loop state spills
+// at 6 and 8, but the pull phase is a chain of dependent loads and wants the threads)
+template <int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_bfs_run(const BfsRunArgs a)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, gth = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n = a.n;
+    for (uint64_t v = gtid; v < n; v += gth) a.level[v] = UNVIS;
+    if (gtid < 3) a.cnt[gtid] = BfsCounters{0, 0, 0, 0};
+    if (gtid == 0) *a.qcur = 0;
+    grid.sync();
+    if (gtid == 0) { a.level[a.src] = 0; a.q0[0] = a.src; }
+    uint64_t nf = 1, mf = a.out_rowptr[a.src + 1] - a.out_rowptr[a.src], m_unvisited = a.m, prev_nf = 0;
+    uint64_t m_reach = mf, inspected = 0;
+    bool pull = false, have_queue = true, have_bitmaps = false;
+    uint32_t *queue = a.q0, *next_q = a.q1, *front = a.bm_front, *next = a.bm_next;
+    int32_t depth = 0;
+    uint32_t levels = 0;
+    grid.sync();
+    while (nf > 0) {
+        depth++;
+        m_unvisited = m_unvisited > mf ? m_unvisited - mf : 0;
+        if (!pull) { if (a.can_pull && mf > m_unvisited / 8 && nf > prev_nf && nf > 1) pull = true; }
+        else if (nf < n / 500 + 1 && nf < prev_nf) pull = false;
+        prev_nf = nf;
+        BfsCounters *cnt = a.cnt + depth % 3;
+        if (gtid == 0) a.cnt[(depth + 1) % 3] = BfsCounters{0, 0, 0, 0}; // last read two barriers ago
+        if (!pull) {
+            if (!have_queue) {
+                const uint64_t nround = (n + 31) & ~31ull;
+                for (uint64_t v = gtid; v < nround; v += gth) {
+                    const bool in = v < n && a.level[v] == depth - 1;
+                    const unsigned mask = __ballot_sync(FULL, in);
+                    if (mask) {
+                        unsigned long long base = 0;
+                        if (lane_id() == 0) base = atomicAdd(a.qcur, (unsigned long long)__popc(mask));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (in) queue[base + __popc(mask & ((1u << lane_id()) - 1u))] = (uint32_t)v;
+                    }
+                }
+                grid.sync();
+                if (gtid == 0) *a.qcur = 0;
+            }
+            bfs_push_phase(a.out_rowptr, a.out_col, queue, nf, a.level, depth, next_q, a.big_row, a.big_begin, cnt);
+            grid.sync();
+            if (cnt->big_count) {
+                bfs_push_big_phase(a.out_rowptr, a.out_col, a.big_row, a.big_begin, a.level, depth, next_q, cnt);
+            }
+            uint32_t *t = queue; queue = next_q; next_q = t;
+            have_queue = true;
+            have_bitmaps = false;
+            inspected += mf;
+        } else {
+            if (!have_bitmaps) { bfs_bitmaps_phase(a.level, n, depth - 1, front, a.bm_vis); grid.sync(); }
+            bfs_pull_phase(a.in_rowptr, a.in_col, a.out_rowptr, n, 0, n, front, a.bm_vis, next, a.level, depth, cnt);
+            if (a.n_long) {
+                grid.sync(); // the long rows OR their bits into words the pass above stored whole
+                bfs_pull_long_phase(a.in_rowptr, a.in_col, a.out_rowptr, a.long_rows, a.n_long, front, a.bm_vis, next, a.level,
+                                    depth, cnt);
+            }
+            uint32_t *t = front; front = next; next = t;
+            have_bitmaps = true;
+            have_queue = false;
+        }
+        grid.sync();
+        const volatile BfsCounters *vc = cnt;
+        if (pull) inspected += vc->next_count;
+        nf = vc->nf;
+        mf = vc->mf;
+        m_reach += mf;
+        levels++;
+    }
+    for (uint64_t v = gtid; v < n; v += gth) { const int32_t l = a.level[v]; a.out[v] = l == UNVIS ? GX_UNREACHED_LEVEL : (int64_t)l; }
+    if (gtid == 0) { a.stats[0] = levels; a.stats[1] = inspected; a.stats[2] = m_reach; }
+}
+
 } // namespace gx
 
 using namespace gx;
@@ -321,7 +431,57 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
         DevBuf<BfsCounters> cnt(1);
         uint64_t m_reach = 0, inspected = 0;
         uint32_t levels = 0;
-        {
+        // GX_BFS_COOP: 0 = host loop; otherwise the shape of the one-launch search, threads per CTA * 10 + CTAs per SM
+        // (fewer, larger CTAs make the grid barrier cheaper: it costs one atomic per CTA)
+        const char *ce = getenv("GX_BFS_COOP");
+        // default: one launch up to 2^23 vertices (RMAT-22: 0.32 -> 0.21 ms); beyond, the pull levels are long enough
+        // that the host loop's full occupancy (2048 threads per SM at 32 registers) wins over its round trips
+        int shape = ce ? atoi(ce) : (n <= (1ull << 23) ? 5122 : 0);
+        struct RunShape { int code, threads, ctas; const void *fn; };
+        static const RunShape shapes[] = {{2564, 256, 4, (const void *)k_bfs_run<256, 4>}, {2568, 256, 8, (const void *)k_bfs_run<256, 8>},
+                                          {5122, 512, 2, (const void *)k_bfs_run<512, 2>}, {5124, 512, 4, (const void *)k_bfs_run<512, 4>},
+                                          {10241, 1024, 1, (const void *)k_bfs_run<1024, 1>}, {10242, 1024, 2, (const void *)k_bfs_run<1024, 2>}};
+        static int coop_ok[6] = {0, 0, 0, 0, 0, 0}; // 0 unknown, 1 co-resident at that shape, -1 not
+        const RunShape *rs = nullptr;
+        int want_ctas = 0;
+        if (!multi() && shape > 0) {
+            int si = 4;
+            for (int i = 0; i < 6; i++) if (shapes[i].code == shape) si = i;
+            if (!coop_ok[si]) {
+                int dev = 0, can = 0, occ = 0;
+                GX_CUDA(cudaGetDevice(&dev));
+                GX_CUDA(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev));
+                GX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shapes[si].fn, shapes[si].threads, 0));
+                coop_ok[si] = (can && occ >= shapes[si].ctas) ? 1 : -1;
+            }
+            if (coop_ok[si] > 0) { rs = &shapes[si]; want_ctas = rs->ctas; }
+        }
+        if (!multi() && want_ctas > 0) {
+            DevBuf<BfsCounters> cnt3(3);
+            DevBuf<unsigned long long> aux(4); // qcur, stats[3]
+            BfsRunArgs a;
+            a.out_rowptr = g->out.rowptr.p; a.out_col = g->out.col.p;
+            a.in_rowptr = can_pull ? in.rowptr.p : nullptr; a.in_col = can_pull ? in.col.p : nullptr;
+            a.long_rows = can_pull ? in.plan.long_rows.p : nullptr; a.n_long = can_pull ? in.plan.n_long : 0;
+            a.n = n; a.m = m; a.src = (uint32_t)src; a.can_pull = can_pull ? 1 : 0;
+            a.level = level.p; a.q0 = q0.p; a.q1 = q1.p; a.bm_front = bm_front.p; a.bm_next = bm_next.p; a.bm_vis = bm_vis.p;
+            a.big_row = big_row.p; a.big_begin = big_begin.p; a.cnt = cnt3.p; a.qcur = aux.p; a.out = g->res_i64.p;
+            a.stats = aux.p + 1;
+            unsigned long long st[3] = {0, 0, 0};
+            {
+                PhaseTimer tk(&c.timing.kernel_ms);
+                void *params[] = {(void *)&a};
+                const bool prof__ = profiling();
+                if (prof__) prof_begin("k_bfs_run");
+                GX_CUDA(cudaLaunchCooperativeKernel(rs->fn, dim3((unsigned)c.num_sms * (unsigned)want_ctas), dim3((unsigned)rs->threads),
+                                                    params, 0, c.stream));
+                if (prof__) prof_end();
+                count_launch();
+                GX_CUDA(cudaMemcpyAsync(c.pinned_scratch, aux.p + 1, sizeof(st), cudaMemcpyDeviceToHost, c.stream));
+            }
+            memcpy(st, c.pinned_scratch, sizeof(st)); // the timer's stop synchronised the stream
+            levels = (uint32_t)st[0]; inspected = st[1]; m_reach = st[2];
+        } else {
             PhaseTimer tk(&c.timing.kernel_ms);
             level.fill_byte(0xFF);
             GX_LAUNCH(k_bfs_seed, 1, 1, 0, level.p, q0.p, (uint32_t)src);
@@ -362,6 +522,9 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
                     if (!have_bitmaps) GX_LAUNCH(k_bfs_bitmaps, grid_persistent(8), 256, 0, level.p, n, depth - 1, front, bm_vis.p);
                     // pull levels are split by row block; push levels (tiny frontiers) run replicated
                     const Partition &part = in.plan.part;
+                    // several GPUs: a rank writes only the words of its row block; with the others zeroed the exchange is
+                    // one all-reduce(max) of n/8 bytes (a group of per-owner broadcasts took 180 us per level on 8 GPUs)
+                    if (multi()) GX_CUDA(cudaMemsetAsync(next, 0, words * sizeof(uint32_t), c.stream));
                     GX_LAUNCH(k_bfs_pull, grid_persistent(8), 256, 0, in.rowptr.p, in.col.p, g->out.rowptr.p, n, part.lo, part.hi,
                               front, bm_vis.p, next, level.p, depth, cnt.p);
                     if (in.plan.n_long)
@@ -369,7 +532,7 @@ extern "C" int gx_bfs(gx_graph *g, uint64_t src, int64_t *level_host)
                                   g->out.rowptr.p, in.plan.long_rows.p, in.plan.n_long, front, bm_vis.p, next, level.p, depth,
                                   cnt.p);
                     if (multi()) {
-                        allgatherv(next, Dt::U32, part, 32, words);
+                        allreduce(next, words, Dt::U32, Red::Max);
                         cnt.zero();
                         GX_LAUNCH(k_bfs_merge, grid_persistent(4), 256, 0, next, bm_vis.p, level.p, g->out.rowptr.p, n,
                                   part.lo / 32, part.hi == n ? words : part.hi / 32, depth, cnt.p);

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--undirected", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare with the CPU oracle (slow at large scale)")
+    ap.add_argument("--cache-at", action="store_true", help="directed graphs: build the in-edge adjacency first (BFS may pull)")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -35,6 +36,8 @@ def main():
     weighted = "sssp" in algos
     t0 = time.perf_counter()
     g = capi.Graph.rmat(args.scale, not args.undirected, weighted=weighted, want_mapping=False)
+    if args.cache_at:
+        g.cache(capi.GX_CACHE_AT)
     src = g.max_degree_vertex()
     print(f"# RMAT-{args.scale} {'undirected' if args.undirected else 'directed'}: n={g.n} nnz={g.nnz} "
           f"|E|={g.num_edges} built in {time.perf_counter() - t0:.2f}s", file=sys.stderr)
