@@ -85,6 +85,12 @@ int gx_graph_create_csr32_cached(gx_graph **g, uint64_t n, uint64_t nnz, const u
  * free with gx_free_host) receives the original vertex ids in dense order. */
 int gx_graph_load(gx_graph **g, const char *dir, int binary, int directed, uint64_t **mapping,
                   uint64_t *n_out);
+/* The text half of ReadMatrixMarket (graphio.cpp:10-24, LAGraph_MMRead of graph.mtx) with the body tokenised ON THE
+ * DEVICE: the file's bytes are copied to HBM as they are, kernels find the entries, parse `row column [value]`
+ * (FP64 values correctly rounded: the same doubles strtod returns) and build the CSR with the same cleaning as the
+ * host parser (self-loops and repeated entries dropped, rows sorted, `symmetric` files mirrored).  `cache` as in
+ * gx_graph_create_csr32_cached.  gx_graph_load uses it for text inputs unless GX_LOADER=host. */
+int gx_graph_load_mtx(gx_graph **g, const char *path, int directed, unsigned cache);
 void gx_free_host(void *p);
 int gx_graph_free(gx_graph *g);
 int gx_graph_info(const gx_graph *g, uint64_t *n, uint64_t *nnz, int *directed, int *weighted);

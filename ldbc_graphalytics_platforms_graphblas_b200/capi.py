@@ -56,6 +56,7 @@ def lib():
             "gx_graph_create_csr32": [pp, u64, u64, vp, vp, vp, i32],
             "gx_graph_create_csr32_cached": [pp, u64, u64, vp, vp, vp, i32, ctypes.c_uint],
             "gx_graph_load": [pp, ctypes.c_char_p, i32, i32, pp, ctypes.POINTER(u64)],
+            "gx_graph_load_mtx": [pp, ctypes.c_char_p, i32, ctypes.c_uint],
             "gx_graph_free": [vp],
             "gx_graph_info": [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(i32), ctypes.POINTER(i32)],
             "gx_graph_cache": [vp, ctypes.c_uint], "gx_graph_download": [vp, vp, vp, vp],
@@ -231,6 +232,13 @@ class Graph:
         mapping = np.ctypeslib.as_array(ctypes.cast(mp, ctypes.POINTER(ctypes.c_uint64)), shape=(n.value,)).copy()
         lib().gx_free_host(mp)
         return cls(h, mapping)
+
+    @classmethod
+    def load_mtx(cls, path, directed, cache=0):
+        """graph.mtx -> device CSR, the text tokenised on the device (no mapping: dense ids)."""
+        h = ctypes.c_void_p()
+        _chk(lib().gx_graph_load_mtx(ctypes.byref(h), os.fsencode(path), int(directed), int(cache)))
+        return cls(h)
 
     @classmethod
     def rmat(cls, scale, directed, weighted=False, seed=None, edgefactor=16, want_mapping=True):

@@ -24,7 +24,6 @@ int main(int argc, char **argv)
 {
     BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
     InitDevice();
-    HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
     auto it = std::find(mapping.begin(), mapping.end(), (GrB_Index)parameters.source_vertex);
@@ -36,9 +35,9 @@ int main(int argc, char **argv)
 
     // as in the reference (bfs.cpp:79-80: neither AT nor the out-degree is cached) nothing derived is built
     // before the timed window; without a cached A' gx_bfs runs push-only on directed graphs, LAGraph's own rule
-    ReserveForGraph(A);
-    gx_graph *G = UploadGraph(A, parameters.directed, 0);
-    PinnedVector<int64_t> result(A.nrows);
+    DeviceGraph D = LoadGraph(parameters, 0);
+    gx_graph *G = D.G;
+    PinnedVector<int64_t> result(D.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     LA_BFS(G, sourceVertex, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

@@ -3,6 +3,7 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "computation_timer.hpp"
@@ -32,6 +33,36 @@ inline gx_graph *UploadGraph(const HostMatrix &A, bool directed, unsigned cache)
     OK(gx_graph_create_csr32_cached(&G, A.nrows, A.nvals, A.Ap.data(), A.Aj.data(), A.iso ? nullptr : A.Ax.data(), directed ? 1 : 0,
                                     cache));
     return G;
+}
+
+// ReadMatrixMarket + the upload in one step for the wrappers that need nothing else from the host matrix.
+// graph.mtx is tokenised on the device (gx_graph_load_mtx: the host reads the header only) unless GX_LOADER=host;
+// graph.grb (--binary true) is read on the host and uploaded.  The device pool is sized for the job either way.
+struct DeviceGraph {
+    gx_graph *G = nullptr;
+    GrB_Index nrows = 0, nvals = 0;
+    bool weighted = false;
+};
+
+inline DeviceGraph LoadGraph(const BenchmarkParameters &parameters, unsigned cache)
+{
+    DeviceGraph D;
+    const char *le = std::getenv("GX_LOADER");
+    if (!parameters.binary && !(le && std::string(le) == "host")) {
+        ComputationTimer timer{"Loading the matrix"};
+        OK(gx_graph_load_mtx(&D.G, (parameters.input_dir + "/graph.mtx").c_str(), parameters.directed ? 1 : 0, cache));
+        uint64_t n = 0, nnz = 0;
+        int weighted = 0;
+        OK(gx_graph_info(D.G, &n, &nnz, nullptr, &weighted));
+        D.nrows = n; D.nvals = nnz; D.weighted = weighted != 0;
+        OK(gx_reserve(4 * (8 * (n + 1) + (weighted ? 12 : 4) * nnz) + 64 * n));
+        return D;
+    }
+    HostMatrix A = ReadMatrixMarket(parameters);
+    ReserveForGraph(A);
+    D.G = UploadGraph(A, parameters.directed, cache);
+    D.nrows = A.nrows; D.nvals = A.nvals; D.weighted = !A.iso;
+    return D;
 }
 
 // Result vector in pinned host memory, allocated before the timed window: the download inside the window then runs

@@ -23,12 +23,11 @@ int main(int argc, char **argv)
 {
     BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
     InitDevice();
-    HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
-    ReserveForGraph(A);
-    gx_graph *G = UploadGraph(A, parameters.directed, 0);
-    PinnedVector<double> result(A.nrows);
+    DeviceGraph D = LoadGraph(parameters, 0);
+    gx_graph *G = D.G;
+    PinnedVector<double> result(D.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     LA_LCC(G, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

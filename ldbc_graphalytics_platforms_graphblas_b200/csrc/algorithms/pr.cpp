@@ -21,15 +21,14 @@ int main(int argc, char **argv)
 {
     BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
     InitDevice();
-    HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
     // the reference transposes inside its timed window (LAGraph_Cached_AT + Cached_OutDegree, pr.cpp:58-61);
     // so does gx_pagerank here: the in-edge adjacency and the tile plan are built on first use, between the
     // two Processing lines
-    ReserveForGraph(A);
-    gx_graph *G = UploadGraph(A, parameters.directed, 0);
-    PinnedVector<double> result(A.nrows);
+    DeviceGraph D = LoadGraph(parameters, 0);
+    gx_graph *G = D.G;
+    PinnedVector<double> result(D.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     LA_PR(G, parameters.damping_factor, parameters.max_iteration, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

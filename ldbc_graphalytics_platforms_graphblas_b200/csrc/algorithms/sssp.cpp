@@ -23,7 +23,6 @@ int main(int argc, char **argv)
 {
     BenchmarkParameters parameters = ParseBenchmarkParameters(argc, argv);
     InitDevice();
-    HostMatrix A = ReadMatrixMarket(parameters);
     std::vector<GrB_Index> mapping = ReadMapping(parameters);
 
     auto it = std::find(mapping.begin(), mapping.end(), (GrB_Index)parameters.source_vertex);
@@ -32,11 +31,11 @@ int main(int argc, char **argv)
         return -1;
     }
     const GrB_Index sourceVertex = (GrB_Index)std::distance(mapping.begin(), it);
-    if (A.iso) throw std::runtime_error("SSSP needs a weighted graph (graph.mtx of type real)");
 
-    ReserveForGraph(A);
-    gx_graph *G = UploadGraph(A, parameters.directed, 0);
-    PinnedVector<double> result(A.nrows);
+    DeviceGraph D = LoadGraph(parameters, 0);
+    gx_graph *G = D.G;
+    if (!D.weighted) throw std::runtime_error("SSSP needs a weighted graph (graph.mtx of type real)");
+    PinnedVector<double> result(D.nrows);
     std::cout << "Processing starts at: " << GetCurrentMilliseconds() << std::endl;
     LA_SSSP(G, sourceVertex, result);
     std::cout << "Processing ends at: " << GetCurrentMilliseconds() << std::endl;

@@ -14,17 +14,27 @@ extern "C" int gx_graph_load(gx_graph **g, const char *dir, int binary, int dire
         p.binary = binary != 0;
         p.input_dir = dir;
         p.directed = directed != 0;
-        HostMatrix A = p.binary ? ReadGrbFile(p.input_dir + "/graph.grb") : ReadMtxFile(p.input_dir + "/graph.mtx");
         std::vector<GrB_Index> map = p.binary ? ReadVtbFile(p.input_dir + "/graph.vtb") : ReadVtxFile(p.input_dir + "/graph.vtx");
-        if (map.size() != A.nrows) return GX_ERR_IO;
-        int rc = gx_graph_create_csr32(g, A.nrows, A.nvals, A.Ap.data(), A.Aj.data(), A.iso ? nullptr : A.Ax.data(), directed);
-        if (rc != GX_OK) return rc;
+        const char *le = std::getenv("GX_LOADER"); // "host": the host-threaded text parser instead of the device tokenizer
+        uint64_t n = 0;
+        if (!p.binary && !(le && std::strcmp(le, "host") == 0)) {
+            const int rc = gx_graph_load_mtx(g, (p.input_dir + "/graph.mtx").c_str(), directed, 0);
+            if (rc != GX_OK) return rc;
+            gx_graph_info(*g, &n, nullptr, nullptr, nullptr);
+            if (map.size() != n) { gx_graph_free(*g); *g = nullptr; return GX_ERR_IO; }
+        } else {
+            HostMatrix A = p.binary ? ReadGrbFile(p.input_dir + "/graph.grb") : ReadMtxFile(p.input_dir + "/graph.mtx");
+            if (map.size() != A.nrows) return GX_ERR_IO;
+            const int rc = gx_graph_create_csr32(g, A.nrows, A.nvals, A.Ap.data(), A.Aj.data(), A.iso ? nullptr : A.Ax.data(), directed);
+            if (rc != GX_OK) return rc;
+            n = A.nrows;
+        }
         if (mapping) {
             *mapping = (uint64_t *)malloc((map.size() ? map.size() : 1) * sizeof(uint64_t));
             if (!*mapping) return GX_ERR_OOM;
             memcpy(*mapping, map.data(), map.size() * sizeof(uint64_t));
         }
-        if (n_out) *n_out = A.nrows;
+        if (n_out) *n_out = n;
         return GX_OK;
     } catch (const std::exception &) {
         return GX_ERR_IO;

@@ -140,3 +140,89 @@ def test_grb_and_mtx_loaders_agree_on_dirty_input(tmp_path):
         assert rc[0].tolist() == [0, 1, 2, 3, 3] and rc[1].tolist() == [1, 2, 0] and rc[2].tolist() == [0.25, 0.75, 1.5]
     finally:
         c.free()
+
+
+# ------------------------------------------------------------------ device tokenizer of graph.mtx (csrc/mtx_device.cu)
+def _messy_mtx(path, n, m, symmetric, weighted, rng):
+    """A graph.mtx in random line order with repeated entries, self-loops, blank lines, CRLF line ends, leading blanks,
+    tabs, several number formats and no newline after the last line."""
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    src[:3000], dst[:3000] = src[3000:6000], dst[3000:6000]      # repeated entries (other weights)
+    src[6000:6200] = dst[6000:6200]                              # self-loops
+    w = rng.random(m) * 100 + 1e-9
+    fmts = ["{:.6f}", "{:.17g}", "{:.16e}", "{:g}", "{!r}", "+{:.3f}", "{:.25f}"]   # the last one has > 19 digits: host fallback
+    lines = []
+    for k, (a, b, x) in enumerate(zip(src.tolist(), dst.tolist(), w.tolist())):
+        val = " 1" if not weighted else " " + fmts[k % len(fmts)].format(x)
+        sep = "\t" if k % 97 == 0 else " "
+        lead = "  " if k % 1013 == 0 else ""
+        end = "\r\n" if k % 31 == 0 else "\n"
+        lines.append(f"{lead}{a + 1}{sep}{b + 1}{val}{end}")
+        if k % 5003 == 0:
+            lines.append("\n")
+    body = "".join(lines).rstrip("\n")
+    kind = "symmetric" if symmetric else "general"
+    field = "real" if weighted else "integer"
+    with open(path, "w", newline="") as f:
+        f.write(f"%%MatrixMarket matrix coordinate {field} {kind}\n%%GraphBLAS {'GrB_FP64' if weighted else 'GrB_BOOL'}\n"
+                f"% a comment line\n{n} {n} {m}\n{body}")
+
+
+@pytest.mark.parametrize("symmetric,weighted", [(False, False), (True, False), (False, True), (True, True)])
+def test_device_and_host_mtx_loaders_build_the_same_graph(tmp_path, monkeypatch, symmetric, weighted):
+    """gx_graph_load tokenises graph.mtx on the device by default; GX_LOADER=host selects the host-threaded parser
+    (ReadMtxFile).  Both must produce bit-identical CSR arrays -- offsets, columns and FP64 weights (the device
+    converts decimals with correct rounding and hands what it cannot decide to strtod)."""
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    capi.init(0)
+    rng = np.random.default_rng(11 + 2 * symmetric + weighted)
+    n, m = 40000, 300000
+    _messy_mtx(tmp_path / "graph.mtx", n, m, symmetric, weighted, rng)
+    (tmp_path / "graph.vtx").write_text("".join(f"{7 + 2 * i}\n" for i in range(n)))
+    monkeypatch.setenv("GX_LOADER", "host")
+    a = capi.Graph.load(str(tmp_path), False, not symmetric)
+    monkeypatch.delenv("GX_LOADER")
+    b = capi.Graph.load(str(tmp_path), False, not symmetric)
+    c = capi.Graph.load_mtx(str(tmp_path / "graph.mtx"), not symmetric, capi.GX_CACHE_AT)
+    try:
+        ra, rb, rc = a.download(), b.download(), c.download()
+        assert a.weighted == weighted and b.weighted == weighted
+        for x, y, z in zip(ra, rb, rc):
+            if x is None:
+                assert y is None and z is None
+            else:
+                assert np.array_equal(x, y) and np.array_equal(x, z)
+        assert np.array_equal(a.mapping, b.mapping)
+        assert np.array_equal(a.wcc(), c.wcc())
+    finally:
+        a.free(); b.free(); c.free()
+
+
+def test_device_mtx_loader_rejects_what_the_host_parser_rejects(tmp_path):
+    from ldbc_graphalytics_platforms_graphblas_b200 import capi
+    capi.init(0)
+    head = "%%MatrixMarket matrix coordinate real general\n%%GraphBLAS GrB_FP64\n"
+    cases = {"too few entries": head + "3 3 3\n1 2 0.5\n2 3 0.5\n",
+             "too many entries": head + "3 3 1\n1 2 0.5\n2 3 0.5\n",
+             "out of range": head + "3 3 2\n1 2 0.5\n2 4 0.5\n",
+             "zero index": head + "3 3 2\n0 2 0.5\n2 3 0.5\n",
+             "no value": head + "3 3 2\n1 2\n2 3 0.5\n",
+             "garbage": head + "3 3 2\n1 x 0.5\n2 3 0.5\n",
+             "not square": head + "3 4 1\n1 2 0.5\n",
+             "not matrix market": "1 2 0.5\n"}
+    for what, text in cases.items():
+        p = tmp_path / "bad.mtx"
+        p.write_text(text)
+        with pytest.raises(capi.GxError):
+            capi.Graph.load_mtx(str(p), True).free()
+    # and the smallest good ones: an empty body, a single entry without a trailing newline
+    p = tmp_path / "ok.mtx"
+    p.write_text(head + "3 3 0\n")
+    g = capi.Graph.load_mtx(str(p), True)
+    assert g.n == 3 and g.nnz == 0
+    g.free()
+    p.write_text(head + "3 3 1\n3 1 1e-3")
+    g = capi.Graph.load_mtx(str(p), True)
+    rp, ci, w = g.download()
+    assert rp.tolist() == [0, 0, 0, 1] and ci.tolist() == [0] and w.tolist() == [0.001]
+    g.free()

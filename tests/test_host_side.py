@@ -223,3 +223,18 @@ def test_relabel_at_scale_and_edge_cases(tmp_path):
         f.write(f"{ids[0]} {int(ids.max()) + 12345}\n")
     with pytest.raises(capi.GxError):
         capi.relabel(str(vp), str(ep), str(out), False, True)
+
+
+def test_device_tokenizer_decimal_conversion_matches_strtod(tmp_path):
+    """csrc/decimal_to_double.cuh (Clinger fast path + Eisel-Lemire, what k_mtx_parse runs per weight) compiled for the
+    host: every double it returns must be the one strtod returns, and the shapes weight files actually carry (%.17g,
+    %.16e, %g of values in (0, 1] and small decimals) must never need the host fallback."""
+    csrc = os.path.join(ROOT, "ldbc_graphalytics_platforms_graphblas_b200", "csrc")
+    exe = tmp_path / "decimal_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", csrc, os.path.join(ROOT, "tests", "decimal_check.cpp"), "-o", str(exe)])
+    r = subprocess.run([str(exe), "800000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    lines = r.stdout.strip().split("\n")
+    assert lines[0].endswith("bad 0")
+    undecided = {int(l.split()[1]): int(l.split()[3]) for l in lines[1:]}
+    assert undecided[1] == 0 and undecided[2] == 0 and undecided[5] == 0 and undecided[7] == 0
