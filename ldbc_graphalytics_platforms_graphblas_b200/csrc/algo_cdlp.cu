@@ -623,6 +623,7 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
         const uint64_t n = g->n;
         if (n == 0) return;
         ensure_in_adj(g);
+        ensure_in_full(g); // several GPUs: the row blocks are balanced over out- and in-entries together, not the in-edge blocks
         if (!g->cdlp_plan) {
             PhaseTimer tb(&c.timing.build_ms);
             g->cdlp_plan = build_cdlp_plan(g);

@@ -313,7 +313,7 @@ extern "C" int gx_wcc(gx_graph *g, uint64_t *comp_host)
         {
             PhaseTimer tb(&c.timing.build_ms);
             ensure_plan(g->out, n);
-            if (g->directed && !out_only) ensure_plan(g->in, n);
+            if (g->directed && !out_only) { ensure_in_full(g); ensure_plan(g->in, n); } // the rest lists walk in-rows of any block
         }
         const uint64_t m_sym = g->directed ? 2 * g->m : g->m;
         g->res_u64.alloc(n);

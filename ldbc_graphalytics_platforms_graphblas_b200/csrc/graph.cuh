@@ -66,6 +66,11 @@ struct gx_graph {
     gx::Adj out;          // CSR: row v = out-neighbours of v
     gx::Adj in;           // CSC: row v = in-neighbours of v (directed only, built lazily)
     bool have_in = false;
+    // several GPUs: after the block-local transposition a rank holds in.rowptr whole but only the in.col entries of its
+    // own row block (in.plan.part) -- all PageRank and the pull levels of BFS ever read; in_block_entries[r] is the first
+    // entry of rank r's block.  ensure_in_full() all-gathers the other blocks for the algorithms that need them.
+    bool in_block_only = false;
+    std::vector<uint64_t> in_block_entries;
 
     // LCC cache: U = A v A' without self-loops, oriented low -> high (degree, id)
     bool have_lcc = false;
@@ -100,6 +105,7 @@ struct gx_graph {
 
 namespace gx {
 void ensure_in_adj(gx_graph *g);   // LAGraph_Cached_AT analogue
+void ensure_in_full(gx_graph *g);  // several GPUs: every rank gets the in.col entries of all row blocks
 void ensure_lcc_cache(gx_graph *g);
 void finish_graph(gx_graph *g);    // validation + row sorting after upload
 void ensure_plan(Adj &a, uint64_t n); // long-row chunk plan of one adjacency
