@@ -41,9 +41,15 @@
 // Algorithmic bytes per iteration: 4m + 8(n+1) + 28n.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "graph.cuh"
 
@@ -189,6 +195,17 @@ struct PrTiles {
     // read evict_first: on RMAT-25 w is 136 MB -- larger than L2 -- and its first third takes 90 % of the gathers.
     uint64_t wps = 0, tps = 0;
     bool hint = false;           // the two-policy gather is compiled in (w larger than about half of L2)
+    // Several GPUs, compact form (3+ ranks): a rank keeps w only for the slots it gathers -- its own segment plus, per
+    // other owner, the slots some row of its block refers to, in slot order: local ids [lbase[o], lbase[o+1]) belong to
+    // owner o.  On RMAT-25 / 8 ranks that is ~40 % of the vector: it stays in L2, and the per-iteration exchange moves
+    // only what is read.  An owner knows what a consumer needs without being told: consumer c needs source v iff v has
+    // an out-entry into c's row block (the out-adjacency is replicated), so both sides derive the same ascending lists.
+    bool compact = false;
+    uint64_t L = 0, Lmax = 0;             // local slots of this rank / the largest over the ranks (equal buffer sizes)
+    uint64_t lbase[MAX_PEERS + 1] = {0};
+    DevBuf<uint32_t> push_list;           // per consumer: offsets inside the own segment, ascending, concatenated
+    uint64_t push_off[MAX_PEERS + 1] = {0};
+    uint64_t push_dst[MAX_PEERS] = {0};   // where this rank's range starts in consumer c's local space
     uint32_t hps = 0, hot = 0;   // hot entries per segment / in total (hps * nranks): the stored ids are h < hot for the
                                  // hottest hps slots of every segment and slot + hot for all others
     PeerBuf wbuf[2];             // the two copies of w (read / written in turn), mapped into all ranks
@@ -283,13 +300,123 @@ __global__ void k_pt_relabel_slice(const uint32_t *__restrict__ col, const uint3
     }
 }
 
-// w0 in the degree-sorted space (replicated on every rank)
+// w0 in the degree-sorted space (replicated on every rank; compact form: only the slots this rank keeps)
 __global__ void k_pt_scatter(const double *__restrict__ w_nat, const uint32_t *__restrict__ pi, uint64_t n,
                              double *__restrict__ w_perm)
 {
     uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; v < n; v += stride) w_perm[pi[v]] = w_nat[v];
+    for (; v < n; v += stride) {
+        const uint32_t s = pi[v];
+        if (s != 0xFFFFFFFFu) w_perm[s] = w_nat[v];
+    }
+}
+
+// ---- compact form ---------------------------------------------------------------------------------------------
+struct RankBounds { uint64_t b[MAX_PEERS + 1]; int nranks; };
+
+__device__ __forceinline__ unsigned owner_of(const RankBounds &rb, uint64_t v)
+{
+    unsigned o = 0;
+    while ((int)o + 1 < rb.nranks && v >= rb.b[o + 1]) o++;
+    return o;
+}
+
+// owner side: which ranks read w[v]?  Bit c is set when v has an out-entry into rank c's row block.  A thread per
+// out-entry of the own vertices (their row ids expanded by a max-scan first); the mask lives at the vertex's offset
+// inside the own segment and is only touched by an atomic when the bit is still missing.
+__global__ void k_pt_row_heads(const uint64_t *__restrict__ rowptr, uint64_t v0, uint64_t v1, uint64_t e0, uint32_t *__restrict__ row_of)
+{
+    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < v1; v += stride) {
+        const uint64_t a = rowptr[v];
+        if (rowptr[v + 1] > a) row_of[a - e0] = (uint32_t)v;
+    }
+}
+
+struct MaxOfU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+__global__ void __launch_bounds__(256)
+k_pt_needmask(const uint32_t *__restrict__ out_col, const uint32_t *__restrict__ row_of, uint64_t count, const RankBounds rb,
+              const uint32_t *__restrict__ pi, uint64_t seg_first, uint32_t *__restrict__ needmask)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < count; e += stride) {
+        const unsigned bit = 1u << owner_of(rb, ld_stream(out_col + e));
+        const uint64_t x = pi[row_of[e]] - seg_first;
+        if (!(needmask[x] & bit)) atomicOr(&needmask[x], bit);
+    }
+}
+
+struct BitOf {
+    unsigned bit;
+    __host__ __device__ uint8_t operator()(uint32_t m) const { return (uint8_t)((m >> bit) & 1u); }
+};
+
+// consumer side: the slots the rows of this rank's block gather from
+__global__ void k_pt_mark_needed(const uint32_t *__restrict__ col, uint64_t count, const uint32_t *__restrict__ pi,
+                                 uint8_t *__restrict__ mark)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < count; e += stride) {
+        const uint32_t s = pi[ld_stream(col + e)];
+        if (!mark[s]) mark[s] = 1; // (most entries find their source marked already: a load instead of a store)
+    }
+}
+
+// pi: global slot -> local id (0xFFFFFFFF for slots this rank does not keep)
+__global__ void k_pt_localise(uint32_t *__restrict__ pi, uint64_t n, const uint8_t *__restrict__ mark, const uint32_t *__restrict__ loc)
+{
+    uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; v < n; v += stride) { const uint32_t s = pi[v]; pi[v] = mark[s] ? loc[s] : 0xFFFFFFFFu; }
+}
+
+struct LocalBases { uint64_t b[MAX_PEERS + 1]; int nranks; };
+
+// stored id of an entry in the compact form: the first hps local slots of every owner's range are the hot stage
+__global__ void k_pt_relabel_compact(const uint32_t *__restrict__ col, const uint32_t *__restrict__ pil, uint64_t count,
+                                     uint64_t padded, uint32_t zero_local, const LocalBases lb, uint32_t hps, uint32_t hot,
+                                     uint32_t *__restrict__ out)
+{
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; e < padded; e += stride) {
+        uint32_t id = zero_local + hot;
+        if (e < count) {
+            const uint32_t l = pil[col[e]];
+            unsigned o = 0;
+            while ((int)o + 1 < lb.nranks && l >= lb.b[o + 1]) o++;
+            const uint32_t j = l - (uint32_t)lb.b[o];
+            id = j < hps ? o * hps + j : l + hot;
+        }
+        out[e] = id;
+    }
+}
+
+// The per-iteration exchange of the compact form: for every consumer, the slots it reads out of this rank's finished
+// segment are gathered (ascending offsets: mostly neighbouring lines) and stored as one contiguous range into the
+// consumer's buffer over NVLink.  Consumer p is served by the CTAs with blockIdx.x % npeer == p.
+struct PushLists {
+    const uint32_t *list[MAX_PEERS - 1];
+    uint64_t count[MAX_PEERS - 1];
+    double *dst[MAX_PEERS - 1];
+    int npeer;
+};
+__global__ void __launch_bounds__(256) k_pr_push_lists(const double *__restrict__ own, const PushLists pl)
+{
+    if (pl.npeer == 0) return;
+    const int p = blockIdx.x % pl.npeer;
+    const unsigned rank_in_peer = blockIdx.x / pl.npeer, ctas_per_peer = gridDim.x / pl.npeer;
+    const uint32_t *__restrict__ list = pl.list[p];
+    double *__restrict__ dst = pl.dst[p];
+    const uint64_t cnt = pl.count[p];
+    for (uint64_t i = (uint64_t)rank_in_peer * 256 + threadIdx.x; i < cnt; i += (uint64_t)ctas_per_peer * 256) dst[i] = own[list[i]];
 }
 
 __global__ void k_pt_tile_k0(const uint64_t *__restrict__ ne_ptr, uint64_t K, uint64_t n_tiles, uint32_t *__restrict__ tile_k0)
@@ -393,6 +520,7 @@ struct PtArgs {
     const double *w;        // degree-sorted space
     const double *w_cold;   // w - hot: stored ids >= hot are slot + hot
     uint32_t hps, wps;      // hot entries per rank segment, slots of a rank's warm piece (PrTiles)
+    uint32_t hot_base[MAX_PEERS]; // first slot of owner o's hottest entries (o * wps; compact form: lbase[o])
     uint32_t warm_end;      // stored ids in [hot, warm_end) ask L2 to keep their lines, the rest are read evict-first
     const double *sink_in;  // sink partials of the previous step (one scalar after the multi-GPU all-reduce)
     unsigned n_sink_in;
@@ -521,7 +649,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1) k_pr_tiles(const PtArgs a)
     // the hottest sources (highest out-degree) are read from shared memory instead of through L1/L2
     for (uint32_t h = threadIdx.x; h < a.hot; h += PT_WARPS * 32) {
         const uint32_t owner = h / a.hps;
-        s_hot[h] = a.w[(uint64_t)owner * a.wps + (h - owner * a.hps)]; // one GPU: w[h]
+        s_hot[h] = a.w[(uint64_t)a.hot_base[owner] + (h - owner * a.hps)]; // one GPU: w[h]
     }
     __syncthreads();
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
@@ -634,6 +762,134 @@ k_pr_tile_fin(const uint32_t *__restrict__ fin_v, const uint32_t *__restrict__ f
     }
 }
 
+// GX_TIMING_DEBUG=1: wall-clock per phase of the plan construction on stderr (rank 0)
+struct PlanLog {
+    bool on = getenv("GX_TIMING_DEBUG") != nullptr && ctx().rank == 0;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(ctx().stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gx timing] PR plan: %-24s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+struct Widen8 {
+    __host__ __device__ uint32_t operator()(uint8_t x) const { return x; }
+};
+
+// compact form: the slots this rank keeps (consumer side), what it sends to whom (owner side), and pi rewritten to
+// local ids.  Collective: the count matrix (owner x consumer) is all-gathered.
+static void build_compact(gx_graph *g, PrTiles *pt, const Adj &in, uint64_t v0, uint64_t v1, uint64_t e0)
+{
+    Context &c = ctx();
+    const int N = c.nranks, r = c.rank;
+    const uint64_t seg = pt->seg, n = g->n, slots = pt->slots;
+    PlanLog log;
+    RankBounds rb;
+    rb.nranks = N;
+    for (int i = 0; i <= N; i++) rb.b[i] = in.plan.part.b[i];
+    // ---- owner side: who reads which of my slots
+    DevBuf<uint32_t> needmask(seg);
+    needmask.zero();
+    if (v1 > v0) {
+        uint64_t oe[2];
+        read_back(&oe[0], g->out.rowptr.p + v0, sizeof(uint64_t));
+        read_back(&oe[1], g->out.rowptr.p + v1, sizeof(uint64_t));
+        const uint64_t cnt = oe[1] - oe[0];
+        if (cnt) {
+            DevBuf<uint32_t> row_of(cnt);
+            GX_CUDA(cudaMemsetAsync(row_of.p, 0, cnt * sizeof(uint32_t), c.stream));
+            GX_LAUNCH(k_pt_row_heads, grid_persistent(8), 256, 0, g->out.rowptr.p, v0, v1, oe[0], row_of.p);
+            size_t tb = 0;
+            GX_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb, row_of.p, row_of.p, MaxOfU32(), (int64_t)cnt, c.stream));
+            DevBuf<char> tmp(tb);
+            GX_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb, row_of.p, row_of.p, MaxOfU32(), (int64_t)cnt, c.stream));
+            count_launch();
+            GX_LAUNCH(k_pt_needmask, grid_persistent(8), 256, 0, g->out.col.p + oe[0], row_of.p, cnt, rb, pt->pi.p, (uint64_t)r * seg,
+                      needmask.p);
+            GX_CUDA(cudaStreamSynchronize(c.stream)); // the scoped buffers
+        }
+    }
+    log.mark("need masks");
+    std::vector<uint64_t> row(N, 0);
+    {
+        DevBuf<uint32_t> lists(seg * (uint64_t)(N - 1));
+        DevBuf<uint64_t> nsel(1);
+        thrust::counting_iterator<uint32_t> ids(0);
+        size_t tb = 0;
+        {
+            auto flags = thrust::make_transform_iterator((const uint32_t *)needmask.p, BitOf{0u});
+            GX_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, ids, flags, lists.p, nsel.p, (int64_t)seg, c.stream));
+        }
+        DevBuf<char> tmp(tb);
+        uint64_t off = 0;
+        for (int cns = 0; cns < N; cns++) {
+            pt->push_off[cns] = off;
+            if (cns == r) { row[cns] = seg; continue; }
+            auto flags = thrust::make_transform_iterator((const uint32_t *)needmask.p, BitOf{(unsigned)cns});
+            GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, ids, flags, lists.p + off, nsel.p, (int64_t)seg, c.stream));
+            count_launch();
+            uint64_t cnt = 0;
+            read_back(&cnt, nsel.p, sizeof(cnt));
+            row[cns] = cnt;
+            off += cnt;
+        }
+        pt->push_off[N] = off;
+        pt->push_list.alloc(off ? off : 1);
+        if (off) GX_CUDA(cudaMemcpyAsync(pt->push_list.p, lists.p, off * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+        GX_CUDA(cudaStreamSynchronize(c.stream)); // `lists` goes out of scope
+    }
+    log.mark("push lists");
+    // ---- everybody's counts: mat[o * N + cns] = slots of owner o that consumer cns keeps
+    std::vector<uint64_t> mat((size_t)N * N);
+    {
+        DevBuf<uint64_t> dm((size_t)N * N);
+        GX_CUDA(cudaMemcpyAsync(dm.p + (size_t)r * N, row.data(), N * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+        allgather_equal(dm.p, Dt::U64, (uint64_t)N);
+        read_back(mat.data(), dm.p, mat.size() * sizeof(uint64_t));
+    }
+    log.mark("count matrix");
+    // ---- consumer side: the slots my rows gather from (+ my own segment), numbered in slot order
+    DevBuf<uint8_t> mark(slots + 1);
+    mark.zero();
+    GX_CUDA(cudaMemsetAsync(mark.p + (uint64_t)r * seg, 1, seg, c.stream));
+    if (pt->M) GX_LAUNCH(k_pt_mark_needed, grid_persistent(8), 256, 0, in.col.p + e0, pt->M, pt->pi.p, mark.p);
+    DevBuf<uint32_t> loc(slots + 1);
+    {
+        auto wide = thrust::make_transform_iterator((const uint8_t *)mark.p, Widen8{});
+        size_t tb = 0;
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, wide, loc.p, (int64_t)(slots + 1), c.stream));
+        DevBuf<char> tmp(tb);
+        GX_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, wide, loc.p, (int64_t)(slots + 1), c.stream));
+        count_launch();
+    }
+    log.mark("mark + scan");
+    for (int o = 0; o <= N; o++) {
+        uint32_t x = 0;
+        read_back(&x, loc.p + (uint64_t)o * seg, sizeof(x));
+        pt->lbase[o] = x;
+    }
+    pt->L = pt->lbase[N];
+    for (int o = 0; o < N; o++)
+        GX_REQUIRE(pt->lbase[o + 1] - pt->lbase[o] == mat[(size_t)o * N + r],
+                   "PageRank compact plan: owner and consumer disagree on the slots to exchange");
+    pt->Lmax = 0;
+    for (int cns = 0; cns < N; cns++) {
+        uint64_t tot = 0;
+        for (int o = 0; o < N; o++) tot += mat[(size_t)o * N + cns];
+        pt->Lmax = std::max(pt->Lmax, tot);
+        uint64_t before = 0;
+        for (int o = 0; o < r; o++) before += mat[(size_t)o * N + cns];
+        pt->push_dst[cns] = before;
+    }
+    GX_LAUNCH(k_pt_localise, grid_persistent(8), 256, 0, pt->pi.p, n, mark.p, loc.p);
+    GX_CUDA(cudaStreamSynchronize(c.stream));
+    log.mark("local ids");
+}
+
 static PrTiles *build_pr_tiles(gx_graph *g)
 {
     PrTiles *pt = new PrTiles();
@@ -696,9 +952,17 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         if (const char *e = getenv("GX_PR_HOT")) hot_cap = (uint32_t)atoi(e) < PT_HOT ? (uint32_t)atoi(e) : PT_HOT; // tuning knob
         pt->hps = (uint32_t)std::min<uint64_t>(seg, hot_cap / (uint32_t)ctx().nranks);
         pt->hot = pt->hps * (uint32_t)ctx().nranks;
+        // compact form (see PrTiles): from 3 ranks on when the peer mapping works; GX_PR_COMPACT=0 / 1 forces it off / on
+        {
+            const char *ce = getenv("GX_PR_COMPACT");
+            bool want = multi() && ctx().nranks <= MAX_PEERS && (ce ? ce[0] != '0' : ctx().nranks >= 3);
+            if (want) want = context_mail().ok; // (collective: every rank evaluates the same condition)
+            pt->compact = want;
+        }
         // warm piece: the often-gathered head of every segment, PR_WARM_MB in total (GX_PR_WARM_MB; 0 = one piece)
         uint64_t warm_mb = PT_WARM_MB;
         if (const char *e = getenv("GX_PR_WARM_MB")) warm_mb = (uint64_t)atoll(e);
+        if (pt->compact) warm_mb = 0; // the kept part of w fits L2: one piece, one load policy
         uint64_t wps = ((warm_mb << 20) / sizeof(double) / (uint64_t)ctx().nranks) & ~31ull;
         wps = std::max<uint64_t>(wps, (pt->hps + 31u) & ~31u);
         if (warm_mb == 0 || wps >= seg) wps = seg;
@@ -708,15 +972,23 @@ static PrTiles *build_pr_tiles(gx_graph *g)
         pt->slots = pt->seg * (uint64_t)ctx().nranks;
         pt->hint = pt->tps > 0 && pt->slots * sizeof(double) > (PT_HINT_MIN_MB << 20);
         if (const char *e = getenv("GX_PR_HINT")) pt->hint = e[0] != '0';
+        if (pt->compact) pt->hint = false;
         GX_REQUIRE(pt->slots + pt->hot < 0xFFFFFFFEull, "vertex slot space exceeds 32 bits");
         GX_LAUNCH(k_pt_make_pi, grid_persistent(8), 256, 0, dk.Current(), dv.Current(), n, bounds.p, pt->wps, pt->tps,
                   (uint64_t)ctx().nranks, pt->pi.p);
     }
+    if (pt->compact) build_compact(g, pt, in, v0, v1, e0);
     // this rank's slice of the column ids as pi(source), tile-aligned at offset 0
     // (padded to whole tiles with the index of a slot that always holds 0: the kernel needs no bounds checks)
     const uint64_t padded = pt->n_tiles * PT_TILE;
     pt->col.alloc(padded ? padded : 1);
-    if (pt->M)
+    if (pt->compact) {
+        LocalBases lb;
+        lb.nranks = ctx().nranks;
+        for (int o = 0; o <= ctx().nranks; o++) lb.b[o] = pt->lbase[o];
+        GX_LAUNCH(k_pt_relabel_compact, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, padded, (uint32_t)pt->L, lb,
+                  pt->hps, pt->hot, pt->col.p);
+    } else if (pt->M)
         GX_LAUNCH(k_pt_relabel_slice, grid_persistent(8), 256, 0, in.col.p + e0, pt->pi.p, pt->M, padded, (uint32_t)pt->slots,
                   (uint32_t)pt->wps, (uint32_t)(pt->wps * (uint64_t)ctx().nranks), pt->hps, pt->hot, pt->col.p);
     pt->tile_k0.alloc(pt->n_tiles ? pt->n_tiles : 1);
@@ -769,9 +1041,14 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GX_CUDA(cudaFuncSetAttribute(tiles_fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PrTiles &ptm = *(PrTiles *)g->pr_cache;
+    // slots of a buffer: the whole index space + the always-zero slot the tile padding gathers; compact form: the
+    // largest local space over the ranks (equal sizes keep the ranks' parked-buffer caches in step) + room for the
+    // hot-stage load to run past a short owner range
+    const uint64_t wcap = pt.compact ? pt.Lmax + pt.hot + 1 : pt.slots + 1;
+    const uint64_t zero_slot = pt.compact ? pt.L : pt.slots;
     if (!ptm.have_wbuf) {
-        peer_alloc(ptm.wbuf[0], (pt.slots + 1) * sizeof(double)); // + the always-zero slot the tile padding gathers
-        peer_alloc(ptm.wbuf[1], (pt.slots + 1) * sizeof(double));
+        peer_alloc(ptm.wbuf[0], wcap * sizeof(double));
+        peer_alloc(ptm.wbuf[1], wcap * sizeof(double));
         ptm.have_wbuf = true;
     }
     // fused exchange (peer stores from the kernels) on 2 GPUs -- measured 4 % ahead of the all-gather there, but
@@ -779,19 +1056,21 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
     // GX_PR_FUSED=0 / 1 forces it off / on.  Never without the peer mapping.
     const char *fe = getenv("GX_PR_FUSED");
     const bool want_fused = fe ? fe[0] != '0' : c.nranks <= 2;
-    const bool fused = multi() && pt.wbuf[0].shared && pt.wbuf[1].shared && want_fused;
+    const bool cpush = pt.compact; // compact form: per-consumer gather lists (k_pr_push_lists)
+    GX_REQUIRE(!cpush || (pt.wbuf[0].shared && pt.wbuf[1].shared), "PageRank compact plan without mapped peer buffers");
+    const bool fused = multi() && !cpush && pt.wbuf[0].shared && pt.wbuf[1].shared && want_fused;
     // otherwise the finished segment is pushed to the peers by one copy kernel (GX_PR_PUSH=0: ncclAllGather)
     const char *pe = getenv("GX_PR_PUSH");
-    const bool push = multi() && !fused && pt.wbuf[0].shared && pt.wbuf[1].shared && !(pe && pe[0] == '0');
+    const bool push = multi() && !cpush && !fused && pt.wbuf[0].shared && pt.wbuf[1].shared && !(pe && pe[0] == '0');
     const uint64_t n_fin = pt.n_span + pt.n_empty;
     DevBuf<double> d(n), w_nat(n), sink_sum(1), tele(1), d_k(pt.K ? pt.K : 1), d_fin(n_fin ? n_fin : 1);
     double *wv[2] = {(double *)pt.wbuf[0].local, (double *)pt.wbuf[1].local};
     if (multi()) { // padding slots are exchanged but never gathered
-        GX_CUDA(cudaMemsetAsync(wv[0], 0, pt.slots * sizeof(double), c.stream));
-        GX_CUDA(cudaMemsetAsync(wv[1], 0, pt.slots * sizeof(double), c.stream));
+        GX_CUDA(cudaMemsetAsync(wv[0], 0, wcap * sizeof(double), c.stream));
+        GX_CUDA(cudaMemsetAsync(wv[1], 0, wcap * sizeof(double), c.stream));
     }
-    GX_CUDA(cudaMemsetAsync(wv[0] + pt.slots, 0, sizeof(double), c.stream)); // the zero slot (never written)
-    GX_CUDA(cudaMemsetAsync(wv[1] + pt.slots, 0, sizeof(double), c.stream));
+    GX_CUDA(cudaMemsetAsync(wv[0] + zero_slot, 0, sizeof(double), c.stream)); // the zero slot (never written)
+    GX_CUDA(cudaMemsetAsync(wv[1] + zero_slot, 0, sizeof(double), c.stream));
     const unsigned g_tiles = (unsigned)c.num_sms;
     const unsigned g_fin = pt.n_span ? grid_for(pt.n_span, 256) : 0; // rows without entries ride along in k_pr_tiles
     const unsigned g_init = grid_persistent(8);
@@ -821,7 +1100,19 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         GX_CUDA(cudaMemcpyAsync(peer_tab.p, h, sizeof(h), cudaMemcpyHostToDevice, c.stream));
         GX_CUDA(cudaStreamSynchronize(c.stream));
     }
-    if (fused || push) {
+    // compact form: what each consumer gets, per buffer (the lists are offsets inside the own segment)
+    PushLists plists[2];
+    for (int b = 0; b < 2; b++) {
+        plists[b].npeer = 0;
+        for (int r = 0; cpush && r < c.nranks; r++) {
+            if (r == c.rank) continue;
+            const int k = plists[b].npeer++;
+            plists[b].list[k] = pt.push_list.p + pt.push_off[r];
+            plists[b].count[k] = pt.push_off[r + 1] - pt.push_off[r];
+            plists[b].dst[k] = (double *)pt.wbuf[b].peer[r] + pt.push_dst[r];
+        }
+    }
+    if (fused || push || cpush) {
         // nobody may store into a rank's buffers before that rank has initialised them
         sink_sum.zero();
         allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
@@ -844,6 +1135,8 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         double *w_old = wv[cur], *w_new = wv[cur ^ 1];
         const WOut *wout = peer_tab.p + (cur ^ 1);
         a.w = w_old; a.w_cold = w_old - hot; a.hps = pt.hps ? pt.hps : 1; a.wps = (uint32_t)pt.wps;
+        for (int r = 0; r < MAX_PEERS; r++)
+            a.hot_base[r] = r < c.nranks ? (uint32_t)(pt.compact ? pt.lbase[r] : (uint64_t)r * pt.wps) : 0u;
         a.warm_end = hot + (uint32_t)(pt.wps * (uint64_t)c.nranks); a.sink_in = sink_in; a.n_sink_in = n_sink_in; a.tele_out = tele.p;
         a.w_new.n = 1;
         a.w_new.p[0] = w_new;
@@ -873,7 +1166,10 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         // the ranks exchange their segments of the new w (their slices of r after the last iteration);
         // a rank's rows are one contiguous segment of the index space w lives in, with the row block's bounds
         if (it + 1 < iters) {
-            if (push) {
+            if (cpush) {
+                const unsigned np = (unsigned)plists[cur ^ 1].npeer;
+                GX_LAUNCH(k_pr_push_lists, np * ((2 * (unsigned)c.num_sms + np - 1) / np), 256, 0, w_new + pt.lbase[c.rank], plists[cur ^ 1]);
+            } else if (push) {
                 const unsigned np = (unsigned)c.nranks - 1;
                 GX_LAUNCH(k_pr_push_segment, np * ((2 * (unsigned)c.num_sms + np - 1) / np), 256, 0, w_new, wout,
                           (uint64_t)c.rank * pt.wps, pt.wps, (uint64_t)c.nranks * pt.wps + (uint64_t)c.rank * pt.tps, pt.tps);

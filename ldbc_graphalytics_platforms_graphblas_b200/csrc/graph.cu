@@ -16,6 +16,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <thrust/iterator/zip_iterator.h>
+#include <thrust/tuple.h>
 
 #include <algorithm>
 #include <chrono>
@@ -416,6 +418,14 @@ __global__ void k_widen_counts(const uint32_t *__restrict__ deg, uint64_t n, uin
     for (; v <= n; v += stride) out[v] = v < n ? deg[v] : 0;
 }
 
+struct ColumnInBlock {
+    uint32_t lo, hi;
+    __host__ __device__ bool operator()(const thrust::tuple<uint32_t, uint32_t> &p) const
+    {
+        return thrust::get<0>(p) >= lo && thrust::get<0>(p) < hi;
+    }
+};
+
 static void transpose_block_local(gx_graph *g)
 {
     Context &c = ctx();
@@ -443,17 +453,18 @@ static void transpose_block_local(gx_graph *g)
     if (mine) {
         DevBuf<uint32_t> keys(mine), vals(mine);
         {
+            // one stable selection over (column, row) pairs: the columns are read once, the rows once
             DevBuf<uint32_t> rows(m);
-            DevBuf<uint8_t> flag(m);
             DevBuf<uint64_t> nsel(1);
             expand_row_ids(g->out.rowptr.p, n, m, rows.p);
-            GX_LAUNCH(k_flag_col_range, grid_persistent(8), 256, 0, g->out.col.p, m, (uint32_t)part.lo, (uint32_t)part.hi, flag.p);
+            auto pairs = thrust::make_zip_iterator(thrust::make_tuple((const uint32_t *)g->out.col.p, (const uint32_t *)rows.p));
+            auto picked = thrust::make_zip_iterator(thrust::make_tuple(keys.p, vals.p));
+            const ColumnInBlock own{(uint32_t)part.lo, (uint32_t)part.hi};
             size_t tb = 0;
-            GX_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, g->out.col.p, flag.p, keys.p, nsel.p, (int64_t)m, c.stream));
+            GX_CUDA(cub::DeviceSelect::If(nullptr, tb, pairs, picked, nsel.p, (int64_t)m, own, c.stream));
             DevBuf<char> tmp(tb);
-            GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, g->out.col.p, flag.p, keys.p, nsel.p, (int64_t)m, c.stream));
-            GX_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, rows.p, flag.p, vals.p, nsel.p, (int64_t)m, c.stream));
-            count_launch(2);
+            GX_CUDA(cub::DeviceSelect::If(tmp.p, tb, pairs, picked, nsel.p, (int64_t)m, own, c.stream));
+            count_launch();
             uint64_t got = 0;
             read_back(&got, nsel.p, sizeof(got));
             GX_REQUIRE(got == mine, "transposition: the selected pairs do not match the in-degree offsets");

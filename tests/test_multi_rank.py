@@ -141,6 +141,54 @@ all_cols = np.concatenate([p[0] for p in parts]); all_rows = np.concatenate([p[1
 assert np.array_equal(all_rows, tci), "column-split transposition: entries"
 assert np.array_equal(np.searchsorted(all_cols, np.arange(n + 1)), trp), "column-split transposition: offsets"
 
+# Block-local transposition (graph.cu transpose_block_local): in-degrees from a histogram of 1/world of the entries,
+# summed over the ranks -> offsets of all in-edge rows and the nnz-balanced row blocks, known everywhere before any
+# sort; a rank then keeps only the in-edge rows of its own block
+es = partition.even_bounds(ci.size, world)
+hist = torch.from_numpy(np.bincount(ci[es[rank]:es[rank + 1]], minlength=n).astype(np.int64)); dist.all_reduce(hist)
+my_trp = np.concatenate([[0], np.cumsum(hist.numpy())])
+assert np.array_equal(my_trp, trp), "block-local transposition: offsets from the in-degree histogram"
+bl = partition.balanced_bounds(my_trp, world)
+keep = (ci >= bl[rank]) & (ci < bl[rank + 1])
+order = np.argsort(ci[keep], kind="stable")
+assert np.array_equal(rows[keep][order], tci[trp[bl[rank]]:trp[bl[rank + 1]]]), "block-local transposition: own block"
+
+# PageRank, compact form (algo_pr.cu build_compact / k_pr_push_lists): a rank keeps w only for its own vertices and for
+# the sources its rows gather from.  The owner derives what a consumer needs from the replicated out-adjacency (v has an
+# out-entry into the consumer's row block), the consumer from its in-edge rows: the same ascending lists on both sides,
+# so the exchange is contiguous ranges and only a count matrix is communicated
+b = partition.balanced_bounds(trp, world)
+lo, hi = b[rank], b[rank + 1]
+owner_of = np.searchsorted(np.asarray(b[1:]), np.arange(n), side="right")
+send = {c: np.array([v for v in range(lo, hi) if c in set(owner_of[ci[rp[v]:rp[v + 1]]].tolist())], dtype=np.int64)
+        for c in range(world) if c != rank}                               # owner side
+mark = np.zeros(n, dtype=bool); mark[lo:hi] = True
+mark[tci[trp[lo]:trp[hi]]] = True                                         # consumer side
+keep_ids = np.nonzero(mark)[0]
+local_of = np.full(n, -1); local_of[keep_ids] = np.arange(keep_ids.size)
+counts = [None] * world
+dist.all_gather_object(counts, {c: int(v.size) for c, v in send.items()})
+for o in range(world):
+    if o != rank:
+        assert counts[o][rank] == int(mark[b[o]:b[o + 1]].sum()), "compact PageRank: owner and consumer disagree"
+w_loc = np.zeros(keep_ids.size)
+r_own = np.full(hi - lo, 1.0 / n)
+r_all = np.full(n, 1.0 / n)
+for it in range(10):
+    sink = torch.tensor([r_own[outdeg[lo:hi] == 0].sum()], dtype=torch.float64); dist.all_reduce(sink)
+    w_own = np.where(outdeg[lo:hi] > 0, r_own / np.where(outdeg[lo:hi] > 0, outdeg[lo:hi] / d, 1.0), 0.0)
+    w_loc[local_of[lo:hi]] = w_own
+    got = [None] * world
+    dist.all_gather_object(got, {c: w_own[v - lo] for c, v in send.items()})   # the pushes of this iteration
+    for o in range(world):
+        if o != rank:
+            w_loc[local_of[b[o]:b[o + 1]][mark[b[o]:b[o + 1]]]] = got[o][rank]   # one contiguous local range per owner
+    tele = (1 - d) / n + d * float(sink) / n
+    r_own = np.array([tele + w_loc[local_of[tci[trp[v]:trp[v + 1]]]].sum() for v in range(lo, hi)])
+r_all[lo:hi] = r_own
+r_all = allgatherv(r_all, b)
+assert np.max(np.abs(r_all - ref) / ref) < 1e-12, "compact PageRank"
+
 # Upload (graph.cu upload_array): equal slices + a common tail cover the array exactly once
 for count in (0, 5, 64 * world, 64 * world + 3, 1000003):
     per, main = partition.upload_slices(count, world)

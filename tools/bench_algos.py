@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--undirected", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare with the CPU oracle (slow at large scale)")
+    ap.add_argument("--hash", action="store_true", help="SHA-256 of the result (to compare a multi-GPU run against this checked one)")
     ap.add_argument("--cache-at", action="store_true", help="directed graphs: build the in-edge adjacency first (BFS may pull)")
     args = ap.parse_args()
     try:
@@ -65,6 +66,9 @@ def main():
                 "hbm_frac": best["algorithmic_bytes"] / (best["kernel_ms"] * 1e-3) / 1e9 / peak,
                 "launches": best["kernel_launches"],
                 "kernels": {k: [v[0], round(v[1], 4)] for k, v in list(prof.items())[:8]}}
+        if args.hash:
+            import hashlib
+            line["sha256"] = hashlib.sha256(run[alg](None).tobytes()).hexdigest()
         if args.check:
             import oracle
             if host is None:

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--scale", type=int, default=24)
     ap.add_argument("--undirected", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--hash", action="store_true", help="SHA-256 of every rank's result (must agree; compare with a checked 1-GPU run)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     dist.init_process_group("gloo")
@@ -52,8 +53,17 @@ def main():
         run[alg]()
         capi.profile(False)
         prof = capi.profile_report()
+        extra = {}
+        if args.hash:
+            import hashlib
+            full = {"bfs": lambda: g.bfs(src), "pr": lambda: g.pagerank(0.85, 10), "wcc": lambda: g.wcc(), "cdlp": lambda: g.cdlp(10),
+                    "lcc": lambda: g.lcc(), "sssp": lambda: g.sssp(src)}[alg]()
+            digest = hashlib.sha256(full.tobytes()).hexdigest()
+            all_d = [None] * world
+            dist.all_gather_object(all_d, digest)
+            extra = {"sha256": digest, "ranks_identical": all(d == digest for d in all_d)}
         if rank == 0:
-            print(json.dumps({"alg": alg, "ranks": world, "scale": args.scale, "n": g.n, "nnz": g.nnz,
+            print(json.dumps({"alg": alg, "ranks": world, "scale": args.scale, "n": g.n, "nnz": g.nnz, **extra,
                               "wall_ms": round(best[0] * 1e3, 3), "kernel_ms": round(best[1]["kernel_ms"], 3),
                               "evps": ev / best[0], "iterations": best[1]["iterations"],
                               "kernels": {k: [v[0], round(v[1], 3)] for k, v in list(prof.items())[:8]}}), flush=True)
