@@ -24,7 +24,10 @@
 // keeps every row's light entries in front (stable partition, built once per graph and delta:
 // SsspCache).  Targets beyond T only get their state marked ("far") and are collected by one
 // pass over the state array when T advances.  delta only schedules work -- the fix-point, hence
-// every bit of the result, is the same.  Several GPUs still run plain sweeps.
+// every bit of the result, is the same.  Several GPUs run the same delta-stepping with owner-held distances:
+// a rank expands the due vertices of its row block, improvements to other ranks' vertices are forwarded by
+// system-scope atomicMin over NVLink peer mappings, and {queue size, smallest waiting distance} are exchanged
+// once per round through peer-mapped mailboxes (sssp_multi_delta below).
 // Algorithmic bytes (one-pass bound): 12m + 8(n+1) + 16n.
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
