@@ -76,18 +76,32 @@ __device__ __forceinline__ int cdlp_bin_of(uint64_t d)
     return d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : d <= CDLP_M_MAX ? 4 : d <= CDLP_C_MAX ? 5 : 6;
 }
 
-__global__ void k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t v0, uint64_t v1,
-                           CdlpLists lists, unsigned long long *__restrict__ counts, int write)
+// (one atomic per bin per 256 rows: a per-row atomic on seven counters ran at 20 GB/s, 1 ms per pass at RMAT-22;
+// the order inside a list is arbitrary here, the lists are sorted afterwards)
+__global__ void __launch_bounds__(256)
+k_cdlp_bin(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t v0, uint64_t v1,
+           CdlpLists lists, unsigned long long *__restrict__ counts, int write)
 {
-    uint64_t v = v0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; v < v1; v += stride) {
-        uint64_t d = rp0[v + 1] - rp0[v];
-        if (rp1) d += rp1[v + 1] - rp1[v];
-        if (d == 0) continue;
+    __shared__ unsigned s_cnt[CDLP_BINS];
+    __shared__ unsigned long long s_base[CDLP_BINS];
+    const uint64_t span = v1 - v0, nround = (span + 255) & ~255ull;
+    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < nround; base += (uint64_t)gridDim.x * 256) {
+        if (threadIdx.x < CDLP_BINS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t v = v0 + base + threadIdx.x;
+        uint64_t d = 0;
+        if (v < v1) {
+            d = rp0[v + 1] - rp0[v];
+            if (rp1) d += rp1[v + 1] - rp1[v];
+        }
         const int b = cdlp_bin_of(d);
-        const unsigned long long pos = atomicAdd(&counts[b], 1ull);
-        if (write) lists.l[b][pos] = (uint32_t)v;
+        unsigned pos = 0;
+        if (d) pos = atomicAdd(&s_cnt[b], 1u);
+        __syncthreads();
+        if (threadIdx.x < CDLP_BINS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (d && write) lists.l[b][s_base[b] + pos] = (uint32_t)v;
+        __syncthreads();
     }
 }
 
@@ -169,6 +183,24 @@ __device__ __forceinline__ void warp_insert(uint32_t *key, uint32_t *cnt, uint32
     if (valid && lane_id() == (unsigned)(__ffs(same) - 1)) smem_insert(key, cnt, mask, lab, __popc(same));
 }
 
+// Labels of the entries k0, k0 + step, ... (U of them) of a row whose first d0 entries come from (col0 + a0) and the
+// rest from (col1 + a1): the U column ids and then the U labels are in flight together -- one trip at a time left a
+// warp waiting on two dependent misses (~1700 cycles) per 32 entries, which, not the tables, bounded these kernels.
+constexpr int CDLP_U = 4;
+__device__ __forceinline__ void cdlp_labels(const uint32_t *__restrict__ col0, uint64_t a0, uint64_t d0,
+                                            const uint32_t *__restrict__ col1, uint64_t a1, uint64_t d, uint64_t k0, uint64_t step,
+                                            const uint32_t *__restrict__ cur, uint32_t (&lab)[CDLP_U])
+{
+    uint32_t c[CDLP_U];
+#pragma unroll
+    for (int j = 0; j < CDLP_U; j++) {
+        const uint64_t k = k0 + (uint64_t)j * step;
+        c[j] = k < d ? (k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0))) : EMPTY;
+    }
+#pragma unroll
+    for (int j = 0; j < CDLP_U; j++) lab[j] = c[j] != EMPTY ? cur[c[j]] : EMPTY;
+}
+
 // bin M: one warp per row, 1024-slot table per warp in shared memory
 constexpr uint32_t CDLP_WT = 1024;
 __global__ void __launch_bounds__(256)
@@ -194,12 +226,12 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
         uint32_t teff = 64;
         while (teff < 2 * d && teff < CDLP_WT) teff <<= 1;
         const uint32_t mask = teff - 1;
-        for (uint64_t base = 0; base < d; base += 32) {
-            const uint64_t k = base + lane;
-            const bool valid = k < d;
-            uint32_t lab = EMPTY;
-            if (valid) lab = cur[k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0))];
-            warp_insert(key, cnt, mask, lab, valid);
+        for (uint64_t base = 0; base < d; base += 32 * CDLP_U) {
+            uint32_t lab[CDLP_U];
+            cdlp_labels(col0, a0, d0, col1, a1, d, base + lane, 32, cur, lab);
+#pragma unroll
+            for (int j = 0; j < CDLP_U; j++)
+                if (base + 32u * j < d) warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY);
         }
         __syncwarp();
         unsigned long long best = 0;
@@ -248,12 +280,12 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
         uint32_t teff = 1024;
         while (teff < 2 * d && teff < CDLP_CT) teff <<= 1;
         const uint32_t mask = teff - 1;
-        for (uint64_t base = 0; base < d; base += 256) {
-            const uint64_t k = base + threadIdx.x;
-            const bool valid = k < d;
-            uint32_t lab = EMPTY;
-            if (valid) lab = cur[k < d0 ? ld_stream(col0 + a0 + k) : ld_stream(col1 + a1 + (k - d0))];
-            warp_insert(key, cnt, mask, lab, valid);
+        for (uint64_t base = 0; base < d; base += 256 * CDLP_U) {
+            uint32_t lab[CDLP_U];
+            cdlp_labels(col0, a0, d0, col1, a1, d, base + threadIdx.x, 256, cur, lab);
+#pragma unroll
+            for (int j = 0; j < CDLP_U; j++)
+                if (base + 256u * j + (threadIdx.x & ~31u) < d) warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY); // warp-uniform
         }
         __syncthreads();
         unsigned long long best = 0;
@@ -311,32 +343,43 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
     const uint64_t e_end = (b0 + CDLP_PIECE < row_end) ? b0 + CDLP_PIECE : row_end;
     const uint64_t t0 = tab_off[li];
     const uint64_t tsize = tab_off[li + 1] - t0;
-    for (uint64_t base = b0; base < e_end; base += 256) {
-        const uint64_t e = base + threadIdx.x;
-        const bool valid = e < e_end;
-        uint32_t lab = EMPTY;
-        if (valid) lab = cur[ld_stream(col + e)];
-        warp_insert(key, cnt, CDLP_CT - 1, lab, valid);
+    for (uint64_t base = b0; base < e_end; base += 256 * CDLP_U) {
+        uint32_t lab[CDLP_U];
+        cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, 256, cur, lab);
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++)
+            if (base + 256u * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
     }
     __syncthreads();
     // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
     // the row has seen is the row's arg-max: one atomicMax per piece, and the slot-parallel scan of the table
     // is only needed to clear it (a memset does that when every row is active).
+    // (CDLP_U slots per trip: their first probes, then their adds, are in flight together)
     unsigned long long best = 0;
-    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) {
-        const uint32_t cc = cnt[i];
-        if (!cc) continue;
-        const uint32_t lab = key[i];
-        uint64_t s = ((uint64_t)hash32(lab) * tsize) >> 32;
-        for (;;) {
-            const uint32_t old = atomicCAS(&gkeys[t0 + s], EMPTY, lab);
-            if (old == EMPTY || old == lab) {
-                const unsigned long long now = (unsigned long long)atomicAdd(&gcnt[t0 + s], cc) + cc;
-                const unsigned long long kk = (now << 32) | (uint32_t)~lab;
-                best = kk > best ? kk : best;
-                break;
+    for (uint32_t i0 = threadIdx.x; i0 < CDLP_CT; i0 += 256 * CDLP_U) {
+        uint32_t cc[CDLP_U], lab[CDLP_U], seen[CDLP_U];
+        uint64_t s[CDLP_U];
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++) {
+            cc[j] = cnt[i0 + 256 * j];
+            lab[j] = key[i0 + 256 * j];
+            s[j] = ((uint64_t)hash32(lab[j]) * tsize) >> 32;
+        }
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? atomicCAS(&gkeys[t0 + s[j]], EMPTY, lab[j]) : EMPTY;
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++)
+            while (seen[j] != EMPTY && seen[j] != lab[j]) { // (only with cc[j] != 0) the slot belongs to another label
+                s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
+                seen[j] = atomicCAS(&gkeys[t0 + s[j]], EMPTY, lab[j]);
             }
-            s = (s + 1 == tsize) ? 0 : s + 1;
+        unsigned long long now[CDLP_U];
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++) now[j] = cc[j] ? (unsigned long long)atomicAdd(&gcnt[t0 + s[j]], cc[j]) + cc[j] : 0ull;
+#pragma unroll
+        for (int j = 0; j < CDLP_U; j++) {
+            const unsigned long long kk = (now[j] << 32) | (uint32_t)~lab[j];
+            if (cc[j] && kk > best) best = kk;
         }
     }
 #pragma unroll
@@ -524,6 +567,17 @@ __global__ void k_widen_u32_cdlp(const uint32_t *__restrict__ in, uint64_t n, ui
     for (; v < n; v += stride) out[v] = in[v];
 }
 
+// {first, last+1} entry of every hub row on both adjacencies
+__global__ void k_cdlp_hub_extents(const uint32_t *__restrict__ listL, uint64_t nL, const uint64_t *__restrict__ rp0,
+                                   const uint64_t *__restrict__ rp1, uint64_t *__restrict__ ext)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nL) return;
+    const uint32_t v = listL[i];
+    ext[4 * i] = rp0[v]; ext[4 * i + 1] = rp0[v + 1];
+    ext[4 * i + 2] = rp1 ? rp1[v] : 0; ext[4 * i + 3] = rp1 ? rp1[v + 1] : 0;
+}
+
 static CdlpPlan *build_cdlp_plan(gx_graph *g)
 {
     CdlpPlan *p = new CdlpPlan();
@@ -550,25 +604,26 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
     // ascending vertex ids: neighbouring list entries then read neighbouring offsets, labels and entries
     for (int b = 0; b < CDLP_BINS - 1; b++) sort_keys32(p->list[b], h[b], bits_for(n));
     if (p->nL) {
-        std::vector<uint32_t> L(p->nL);
-        std::vector<uint64_t> h0(n + 1), h1;
+        // the hub rows' extents come back from the device (a few thousand rows: the offsets of all n rows used to be
+        // copied to the host for this, 19 ms of a 41 ms plan at RMAT-24); the piece lists are laid out on the host
         cudaStream_t s = ctx().stream;
-        GX_CUDA(cudaMemcpyAsync(L.data(), p->listL.p, p->nL * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        GX_CUDA(cudaMemcpyAsync(h0.data(), rp0, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        if (rp1) { h1.resize(n + 1); GX_CUDA(cudaMemcpyAsync(h1.data(), rp1, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s)); }
+        sort_keys32(p->listL, p->nL, bits_for(n));
+        DevBuf<uint64_t> ext(4 * p->nL);
+        GX_LAUNCH(k_cdlp_hub_extents, grid_for(p->nL, 256), 256, 0, p->listL.p, p->nL, rp0, rp1, ext.p);
+        std::vector<uint64_t> hx(4 * p->nL);
+        GX_CUDA(cudaMemcpyAsync(hx.data(), ext.p, 4 * p->nL * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         GX_CUDA(cudaStreamSynchronize(s));
-        std::sort(L.begin(), L.end());
         std::vector<uint64_t> tab_off(p->nL + 1), ins_begin, scan_begin;
         std::vector<uint32_t> ins_row, scan_row;
         std::vector<uint8_t> ins_side;
         uint64_t off = 0;
         for (uint64_t i = 0; i < p->nL; i++) {
-            const uint32_t v = L[i];
-            uint64_t d = h0[v + 1] - h0[v];
-            for (uint64_t b = h0[v]; b < h0[v + 1]; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(0); ins_begin.push_back(b); }
+            const uint64_t a0 = hx[4 * i], b0 = hx[4 * i + 1], a1 = hx[4 * i + 2], b1 = hx[4 * i + 3];
+            uint64_t d = b0 - a0;
+            for (uint64_t b = a0; b < b0; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(0); ins_begin.push_back(b); }
             if (rp1) {
-                d += h1[v + 1] - h1[v];
-                for (uint64_t b = h1[v]; b < h1[v + 1]; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(1); ins_begin.push_back(b); }
+                d += b1 - a1;
+                for (uint64_t b = a1; b < b1; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(1); ins_begin.push_back(b); }
             }
             tab_off[i] = off;
             for (uint64_t sb = off; sb < off + 2 * d; sb += SCAN_CHUNK) { scan_row.push_back((uint32_t)i); scan_begin.push_back(sb); }
@@ -582,7 +637,6 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
         p->ins_row.alloc(p->n_ins); p->ins_side.alloc(p->n_ins); p->ins_begin.alloc(p->n_ins);
         p->scan_row.alloc(p->n_scan); p->scan_begin.alloc(p->n_scan);
         p->gkeys.alloc(off); p->gcnt.alloc(off); p->best.alloc(p->nL);
-        GX_CUDA(cudaMemcpyAsync(p->listL.p, L.data(), p->nL * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->tab_off.p, tab_off.data(), (p->nL + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_row.p, ins_row.data(), p->n_ins * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_side.p, ins_side.data(), p->n_ins * sizeof(uint8_t), cudaMemcpyHostToDevice, s));

@@ -108,6 +108,19 @@ __global__ void k_pr_tele(const double *__restrict__ sink_part, unsigned nparts,
     if (threadIdx.x == 0) *sink_sum = x;
 }
 
+// the same with the all-reduce inside: the partial goes through the peer mailboxes (comm.cuh), ~45 us of NCCL launch
+// + protocol per iteration on 8 GPUs become one NVLink round trip, and the host queues the whole loop without waiting
+__global__ void k_pr_tele_mail(const double *__restrict__ sink_part, unsigned nparts, double *__restrict__ sink_sum, MailTable t,
+                               unsigned long long seq)
+{
+    __shared__ double s_red[33];
+    const double x = block_sum_ordered(sink_part, nparts, s_red);
+    if (threadIdx.x < 32) {
+        const double s = peer_mail_sum_f64(t, x, seq);
+        if (threadIdx.x == 0) *sink_sum = s;
+    }
+}
+
 struct PrScalars { double teleport, damping, n; };
 
 // Where a new w' value goes: this rank's copy and, on several GPUs, every peer's copy of the vector
@@ -1117,13 +1130,23 @@ static void pagerank_tiles(gx_graph *g, double damping, int iters)
         sink_sum.zero();
         allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
     }
+    // the per-iteration sum of the sink mass, which is also the barrier: peer mailboxes (GX_PR_MAIL=0: NCCL all-reduce)
+    PeerMail *mail = nullptr;
+    if (multi() && c.nranks <= MAX_PEERS) {
+        const char *me = getenv("GX_PR_MAIL");
+        if (!(me && me[0] == '0')) mail = &context_mail();
+    }
     for (int it = 0; it < iters; it++) {
         const double *sink_in = s_in;
         unsigned n_sink_in = nparts;
         if (multi()) {
             // the sink mass is spread over the ranks: fold the local partials, all-reduce the scalar
-            GX_LAUNCH(k_pr_tele, 1, 256, 0, s_in, nparts, sink_sum.p);
-            allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
+            if (mail && mail->ok) {
+                GX_LAUNCH(k_pr_tele_mail, 1, 256, 0, s_in, nparts, sink_sum.p, mail->table, ++mail->seq);
+            } else {
+                GX_LAUNCH(k_pr_tele, 1, 256, 0, s_in, nparts, sink_sum.p);
+                allreduce(sink_sum.p, 1, Dt::F64, Red::Sum);
+            }
             sink_in = sink_sum.p;
             n_sink_in = 1;
         }

@@ -109,6 +109,35 @@ __device__ __forceinline__ void peer_mail_exchange(const MailTable &t, unsigned 
         h[3] = bad ? ~0ull : seq;
     }
 }
+
+// Same mailboxes, result kept on the device: every rank's double summed in rank order -- the same bits on every rank --
+// and, like the exchange above, a barrier (a peer's word arrives after that peer's earlier kernels on its stream, i.e.
+// after all its peer stores).  No host involvement: an iteration loop can queue these back to back.  One warp.
+__device__ __forceinline__ double peer_mail_sum_f64(const MailTable &t, double x, unsigned long long seq)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned par = (unsigned)(seq & 1ull);
+    if ((int)lane < t.nranks) {
+        volatile unsigned long long *slot = t.peer[lane] + ((size_t)par * MAX_PEERS + t.rank) * MAIL_WORDS;
+        slot[0] = (unsigned long long)__double_as_longlong(x);
+        __threadfence_system();
+        slot[2] = seq;
+    }
+    double v = 0.0;
+    bool bad = false;
+    if ((int)lane < t.nranks) {
+        volatile unsigned long long *mine = t.peer[t.rank] + ((size_t)par * MAX_PEERS + lane) * MAIL_WORDS;
+        const long long t0 = clock64();
+        while (mine[2] != seq)
+            if (clock64() - t0 > 8000000000ll) { bad = true; break; } // ~4 s: a peer died
+        __threadfence_system();
+        v = __longlong_as_double((long long)mine[0]);
+    }
+    if (__any_sync(0xffffffffu, bad)) __trap(); // surfaces as a CUDA error at the caller's next synchronisation
+    double sum = 0.0;
+    for (int r = 0; r < t.nranks; r++) sum += __shfl_sync(0xffffffffu, v, r);
+    return sum;
+}
 #endif
 
 enum class Red { Sum, Min, Max };
