@@ -40,8 +40,12 @@
 namespace gx {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr int CDLP_BINS = 7; // T4 T8 T16 T32 M C H
+constexpr int CDLP_BINS = 10; // T4 T8 T16 T32 | M1 M2 | C1 C2 C3 | H
 constexpr uint32_t CDLP_M_MAX = 512, CDLP_C_MAX = 4096;
+// The table of a bin is sized for the bin's longest row: a CTA's shared memory, hence the warps an SM keeps in flight,
+// follows the bin -- every row is a chain of dependent misses (offsets -> column ids -> labels) that only other rows
+// can overlap.  One 1024-slot table per warp / 8192-slot table per CTA for all of M / C kept 24 warps per SM.
+constexpr uint32_t CDLP_M1_MAX = 128, CDLP_C1_MAX = 1024, CDLP_C2_MAX = 2048;
 constexpr uint32_t CDLP_PIECE = 4096;  // hub entries per CTA
 constexpr uint32_t CDLP_CT = 8192;     // slots of the CTA-wide shared-memory table (64 KB)
 constexpr uint32_t SCAN_CHUNK = 8192;  // global table slots per CTA in the arg-max pass
@@ -50,7 +54,7 @@ struct CdlpPlan {
     bool built = false;
     bool first_closed_form = false; // undirected, no repeated entries: iteration 1 is "smallest neighbour"
     Partition part; // row blocks balanced by entries (out + in)
-    uint64_t nb[CDLP_BINS] = {0, 0, 0, 0, 0, 0, 0}; // rows per bin
+    uint64_t nb[CDLP_BINS] = {0}; // rows per bin
     uint64_t nL = 0, n_ins = 0, n_scan = 0, slots = 0; // L = hub rows (bin H)
     DevBuf<uint32_t> list[CDLP_BINS - 1], listL;
     DevBuf<uint64_t> tab_off;      // nL + 1: first slot of each L row's table
@@ -59,7 +63,8 @@ struct CdlpPlan {
     DevBuf<uint64_t> ins_begin;    // first entry of the chunk
     DevBuf<uint32_t> scan_row;     // scan chunks: index into listL
     DevBuf<uint64_t> scan_begin;   // first slot of the chunk
-    DevBuf<uint32_t> gkeys, gcnt;  // global tables
+    DevBuf<uint2> gtab;            // global tables: slot = {label + 1 (0 = empty), count}, one 8-byte word, so that the
+                                   // claim of a slot and the add that follows touch one DRAM sector and one memset clears both
     DevBuf<unsigned long long> best; // nL arg-max accumulators
 };
 
@@ -73,7 +78,8 @@ struct CdlpLists { uint32_t *l[CDLP_BINS]; };
 
 __device__ __forceinline__ int cdlp_bin_of(uint64_t d)
 {
-    return d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : d <= CDLP_M_MAX ? 4 : d <= CDLP_C_MAX ? 5 : 6;
+    return d <= 4 ? 0 : d <= 8 ? 1 : d <= 16 ? 2 : d <= 32 ? 3 : d <= CDLP_M1_MAX ? 4 : d <= CDLP_M_MAX ? 5
+         : d <= CDLP_C1_MAX ? 6 : d <= CDLP_C2_MAX ? 7 : d <= CDLP_C_MAX ? 8 : 9;
 }
 
 // (one atomic per bin per 256 rows: a per-row atomic on seven counters ran at 20 GB/s, 1 ms per pass at RMAT-22;
@@ -164,23 +170,39 @@ k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *_
     if (ch) *changed = 1;
 }
 
-// add `n` occurrences of `lab` to an open-addressing table (power-of-two size) in shared memory
-__device__ __forceinline__ void smem_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, uint32_t n)
+// add `n` occurrences of `lab` to an open-addressing table (power-of-two size) in shared memory; returns the label's
+// count after the add
+__device__ __forceinline__ uint32_t smem_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, uint32_t n)
 {
     uint32_t s = hash32(lab) & mask;
     for (;;) {
         uint32_t seen = ((volatile uint32_t *)key)[s];
         if (seen == EMPTY) seen = atomicCAS(&key[s], EMPTY, lab);
-        if (seen == EMPTY || seen == lab) { atomicAdd(&cnt[s], n); break; }
+        if (seen == EMPTY || seen == lab) return atomicAdd(&cnt[s], n) + n;
         s = (s + 1) & mask;
     }
 }
 
-// lanes of a warp that hold the same label elect one lane to insert it with the multiplicity
-__device__ __forceinline__ void warp_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, bool valid)
+// lanes of a warp that hold the same label elect one lane to insert it with the multiplicity.  Returns the arg-max
+// key (count << 32 | ~label) of the count that add produced, 0 on the other lanes: the add that completes a label's
+// count returns the full count, so the largest key any add of a row has returned is the row's arg-max and the table
+// never has to be scanned -- it is cleared with vector stores (the scan of 2-4 slots per entry cost as much as the
+// inserts themselves).
+__device__ __forceinline__ unsigned long long warp_insert(uint32_t *key, uint32_t *cnt, uint32_t mask, uint32_t lab, bool valid)
 {
     const unsigned same = __match_any_sync(FULL, valid ? lab : EMPTY);
-    if (valid && lane_id() == (unsigned)(__ffs(same) - 1)) smem_insert(key, cnt, mask, lab, __popc(same));
+    if (valid && lane_id() == (unsigned)(__ffs(same) - 1))
+        return ((unsigned long long)smem_insert(key, cnt, mask, lab, __popc(same)) << 32) | (uint32_t)~lab;
+    return 0ull;
+}
+
+// slots [0, teff) of a table back to empty: `nthreads` threads (this one is `t`), 4 slots per store; teff is a multiple of 4
+__device__ __forceinline__ void smem_table_clear(uint32_t *key, uint32_t *cnt, uint32_t teff, uint32_t t, uint32_t nthreads)
+{
+    for (uint32_t s = 4 * t; s < teff; s += 4 * nthreads) {
+        *(uint4 *)(key + s) = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        *(uint4 *)(cnt + s) = make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // Labels of the entries k0, k0 + step, ... (U of them) of a row whose first d0 entries come from (col0 + a0) and the
@@ -201,15 +223,15 @@ __device__ __forceinline__ void cdlp_labels(const uint32_t *__restrict__ col0, u
     for (int j = 0; j < CDLP_U; j++) lab[j] = c[j] != EMPTY ? cur[c[j]] : EMPTY;
 }
 
-// bin M: one warp per row, 1024-slot table per warp in shared memory
-constexpr uint32_t CDLP_WT = 1024;
+// bins M1 / M2: one warp per row, a WT-slot table per warp in shared memory (WT >= 2 x the bin's longest row)
+template <uint32_t CDLP_WT>
 __global__ void __launch_bounds__(256)
 k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
                  const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
                  const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
                  int *__restrict__ changed)
 {
-    extern __shared__ uint32_t s_tab[];
+    extern __shared__ __align__(16) uint32_t s_tab[];
     for (uint32_t i = threadIdx.x; i < 8 * CDLP_WT * 2; i += 256) s_tab[i] = (i < 8 * CDLP_WT) ? EMPTY : 0u;
     __syncthreads();
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
@@ -226,24 +248,19 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
         uint32_t teff = 64;
         while (teff < 2 * d && teff < CDLP_WT) teff <<= 1;
         const uint32_t mask = teff - 1;
+        unsigned long long best = 0;
         for (uint64_t base = 0; base < d; base += 32 * CDLP_U) {
             uint32_t lab[CDLP_U];
             cdlp_labels(col0, a0, d0, col1, a1, d, base + lane, 32, cur, lab);
 #pragma unroll
             for (int j = 0; j < CDLP_U; j++)
-                if (base + 32u * j < d) warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY);
+                if (base + 32u * j < d) {
+                    const unsigned long long kk = warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY);
+                    best = kk > best ? kk : best;
+                }
         }
         __syncwarp();
-        unsigned long long best = 0;
-        for (uint32_t s = lane; s < teff; s += 32) {
-            const uint32_t c = cnt[s];
-            if (c) {
-                const unsigned long long kk = ((unsigned long long)c << 32) | (uint32_t)~key[s];
-                best = kk > best ? kk : best;
-                key[s] = EMPTY;
-                cnt[s] = 0;
-            }
-        }
+        smem_table_clear(key, cnt, teff, lane, 32);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long x = __shfl_xor_sync(FULL, best, o);
@@ -259,17 +276,18 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
     if (ch) *changed = 1;
 }
 
-// bin C: one CTA per row, CDLP_CT-slot table in shared memory
+// bins C1 / C2 / C3: one CTA per row, a CT-slot table in shared memory (CT >= 2 x the bin's longest row)
+template <uint32_t CT>
 __global__ void __launch_bounds__(256)
 k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
                 const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
                 const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
                 int *__restrict__ changed)
 {
-    extern __shared__ uint32_t s_tab[];
-    uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    uint32_t *key = s_tab, *cnt = s_tab + CT;
     __shared__ unsigned long long s_best[8];
-    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
+    for (uint32_t i = threadIdx.x; i < CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
     __syncthreads();
     for (uint64_t r = blockIdx.x; r < count; r += gridDim.x) {
         const uint32_t v = list[r];
@@ -278,26 +296,21 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
         uint64_t a1 = 0, d = d0;
         if (rp1) { a1 = rp1[v]; d += rp1[v + 1] - a1; }
         uint32_t teff = 1024;
-        while (teff < 2 * d && teff < CDLP_CT) teff <<= 1;
+        while (teff < 2 * d && teff < CT) teff <<= 1;
         const uint32_t mask = teff - 1;
+        unsigned long long best = 0;
         for (uint64_t base = 0; base < d; base += 256 * CDLP_U) {
             uint32_t lab[CDLP_U];
             cdlp_labels(col0, a0, d0, col1, a1, d, base + threadIdx.x, 256, cur, lab);
 #pragma unroll
             for (int j = 0; j < CDLP_U; j++)
-                if (base + 256u * j + (threadIdx.x & ~31u) < d) warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY); // warp-uniform
+                if (base + 256u * j + (threadIdx.x & ~31u) < d) { // warp-uniform
+                    const unsigned long long kk = warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY);
+                    best = kk > best ? kk : best;
+                }
         }
         __syncthreads();
-        unsigned long long best = 0;
-        for (uint32_t s = threadIdx.x; s < teff; s += 256) {
-            const uint32_t c = cnt[s];
-            if (c) {
-                const unsigned long long kk = ((unsigned long long)c << 32) | (uint32_t)~key[s];
-                best = kk > best ? kk : best;
-                key[s] = EMPTY;
-                cnt[s] = 0;
-            }
-        }
+        smem_table_clear(key, cnt, teff, threadIdx.x, 256);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long x = __shfl_xor_sync(FULL, best, o);
@@ -323,10 +336,9 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
                   const uint8_t *__restrict__ ins_side, const uint64_t *__restrict__ ins_begin,
                   const uint64_t *__restrict__ tab_off, const uint64_t *__restrict__ rp0, const uint32_t *__restrict__ col0,
                   const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1, const uint32_t *__restrict__ cur,
-                  const uint8_t *__restrict__ active, uint32_t *__restrict__ gkeys, uint32_t *__restrict__ gcnt,
-                  unsigned long long *__restrict__ best_out)
+                  const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, unsigned long long *__restrict__ best_out)
 {
-    extern __shared__ uint32_t s_tab[];
+    extern __shared__ __align__(16) uint32_t s_tab[];
     uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
     __shared__ unsigned long long s_best[8];
     const uint32_t c = blockIdx.x;
@@ -354,28 +366,49 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
     // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
     // the row has seen is the row's arg-max: one atomicMax per piece, and the slot-parallel scan of the table
     // is only needed to clear it (a memset does that when every row is active).
-    // (CDLP_U slots per trip: their first probes, then their adds, are in flight together)
+    // Each warp owns 1/8 of the table.  It first compacts its non-empty slots to the front of its share (in place: the
+    // write position never passes the read position), so that every lane of every later trip has work -- with a few
+    // hundred distinct labels per piece most trips of the strided walk waited two dependent L2-miss atomics for one or two
+    // lanes.  Then the target lines of all its (label, count) pairs are prefetched into L2, and only then come the
+    // atomics: CDLP_U claims in flight per lane, then their adds (same 8-byte slot, now an L2 hit).
+    constexpr uint32_t SHARE = CDLP_CT / 8;
+    const unsigned lane = lane_id();
+    uint32_t *wkey = key + (threadIdx.x >> 5) * SHARE, *wcnt = cnt + (threadIdx.x >> 5) * SHARE;
+    uint32_t nw = 0;
+    for (uint32_t i = lane; i < SHARE; i += 32) {
+        const uint32_t cc = wcnt[i], lab = wkey[i];
+        const unsigned m = __ballot_sync(FULL, cc != 0);
+        __syncwarp();
+        if (cc) { const uint32_t d = nw + __popc(m & ((1u << lane) - 1u)); wkey[d] = lab; wcnt[d] = cc; }
+        nw += __popc(m);
+        __syncwarp();
+    }
+    for (uint32_t i = lane; i < nw; i += 32) {
+        const uint64_t sl = ((uint64_t)hash32(wkey[i]) * tsize) >> 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gtab + t0 + sl));
+    }
     unsigned long long best = 0;
-    for (uint32_t i0 = threadIdx.x; i0 < CDLP_CT; i0 += 256 * CDLP_U) {
+    for (uint32_t i0 = lane; i0 < nw; i0 += 32 * CDLP_U) {
         uint32_t cc[CDLP_U], lab[CDLP_U], seen[CDLP_U];
         uint64_t s[CDLP_U];
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++) {
-            cc[j] = cnt[i0 + 256 * j];
-            lab[j] = key[i0 + 256 * j];
+            const bool have = i0 + 32 * j < nw;
+            cc[j] = have ? wcnt[i0 + 32 * j] : 0u;
+            lab[j] = have ? wkey[i0 + 32 * j] : EMPTY;
             s[j] = ((uint64_t)hash32(lab[j]) * tsize) >> 32;
         }
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? atomicCAS(&gkeys[t0 + s[j]], EMPTY, lab[j]) : EMPTY;
+        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? atomicCAS(&gtab[t0 + s[j]].x, 0u, lab[j] + 1u) - 1u : EMPTY;
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++)
             while (seen[j] != EMPTY && seen[j] != lab[j]) { // (only with cc[j] != 0) the slot belongs to another label
                 s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
-                seen[j] = atomicCAS(&gkeys[t0 + s[j]], EMPTY, lab[j]);
+                seen[j] = atomicCAS(&gtab[t0 + s[j]].x, 0u, lab[j] + 1u) - 1u;
             }
         unsigned long long now[CDLP_U];
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) now[j] = cc[j] ? (unsigned long long)atomicAdd(&gcnt[t0 + s[j]], cc[j]) + cc[j] : 0ull;
+        for (int j = 0; j < CDLP_U; j++) now[j] = cc[j] ? (unsigned long long)atomicAdd(&gtab[t0 + s[j]].y, cc[j]) + cc[j] : 0ull;
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++) {
             const unsigned long long kk = (now[j] << 32) | (uint32_t)~lab[j];
@@ -400,8 +433,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
 __global__ void __launch_bounds__(256)
 k_cdlp_big_scan(const uint32_t *__restrict__ listL, const uint32_t *__restrict__ scan_row,
                 const uint64_t *__restrict__ scan_begin, const uint64_t *__restrict__ tab_off,
-                const uint8_t *__restrict__ active, uint32_t *__restrict__ gkeys, uint32_t *__restrict__ gcnt,
-                unsigned long long *__restrict__ best_out)
+                const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, unsigned long long *__restrict__ best_out)
 {
     const uint32_t c = blockIdx.x;
     const uint32_t li = scan_row[c];
@@ -411,17 +443,16 @@ k_cdlp_big_scan(const uint32_t *__restrict__ listL, const uint32_t *__restrict__
     const uint64_t s_end = (s0 + SCAN_CHUNK < t_end) ? s0 + SCAN_CHUNK : t_end;
     unsigned long long best = 0;
     for (uint64_t sb = s0 + threadIdx.x; sb < s_end; sb += 256 * 8) {
-        uint32_t cc[8];
+        uint2 cc[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const uint64_t q = sb + (uint64_t)j * 256; cc[j] = q < s_end ? __ldcg(gcnt + q) : 0u; }
+        for (int j = 0; j < 8; j++) { const uint64_t q = sb + (uint64_t)j * 256; cc[j] = q < s_end ? __ldcg(gtab + q) : make_uint2(0u, 0u); }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (cc[j]) {
+            if (cc[j].x) {
                 const uint64_t q = sb + (uint64_t)j * 256;
-                const unsigned long long kk = ((unsigned long long)cc[j] << 32) | (uint32_t)~__ldcg(gkeys + q);
+                const unsigned long long kk = ((unsigned long long)cc[j].y << 32) | (uint32_t)~(cc[j].x - 1u);
                 best = kk > best ? kk : best;
-                gkeys[q] = EMPTY;
-                gcnt[q] = 0;
+                gtab[q] = make_uint2(0u, 0u);
             }
         }
     }
@@ -636,15 +667,14 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
         p->tab_off.alloc(p->nL + 1);
         p->ins_row.alloc(p->n_ins); p->ins_side.alloc(p->n_ins); p->ins_begin.alloc(p->n_ins);
         p->scan_row.alloc(p->n_scan); p->scan_begin.alloc(p->n_scan);
-        p->gkeys.alloc(off); p->gcnt.alloc(off); p->best.alloc(p->nL);
+        p->gtab.alloc(off); p->best.alloc(p->nL);
         GX_CUDA(cudaMemcpyAsync(p->tab_off.p, tab_off.data(), (p->nL + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_row.p, ins_row.data(), p->n_ins * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_side.p, ins_side.data(), p->n_ins * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_begin.p, ins_begin.data(), p->n_ins * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->scan_row.p, scan_row.data(), p->n_scan * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->scan_begin.p, scan_begin.data(), p->n_scan * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        p->gkeys.fill_byte(0xFF);
-        p->gcnt.zero();
+        p->gtab.zero();
         p->best.zero();
         GX_CUDA(cudaStreamSynchronize(s));
     }
@@ -685,9 +715,9 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
         CdlpPlan &p = *(CdlpPlan *)g->cdlp_plan;
         const uint64_t *rp0 = g->out.rowptr.p, *rp1 = g->directed ? g->in.rowptr.p : nullptr;
         const uint32_t *col0 = g->out.col.p, *col1 = g->directed ? g->in.col.p : nullptr;
-        constexpr size_t SMEM_M = (size_t)8 * CDLP_WT * 8, SMEM_C = (size_t)CDLP_CT * 8;
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_warp_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_M));
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
+        constexpr size_t SMEM_C = (size_t)CDLP_CT * 8;
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_warp_rows<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8));
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows<CDLP_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
         GX_CUDA(cudaFuncSetAttribute(k_cdlp_big_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
         g->res_u64.alloc(n);
         const uint64_t m_eff = g->directed ? 2 * g->m : g->m;
@@ -715,22 +745,27 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                 } else {
                 if (p.nL) {
                     GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, 256, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
-                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gkeys.p, p.gcnt.p, p.best.p);
+                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gtab.p, p.best.p);
                     if (!act) {
-                        // every hub row was filled: clearing the tables is two memsets (the scan costs 5 ms per
+                        // every hub row was filled: clearing the tables is one memset (the scan costs 5 ms per
                         // iteration while the labels are still many)
-                        p.gkeys.fill_byte(0xFF);
-                        p.gcnt.zero();
+                        p.gtab.zero();
                     } else {
                         GX_LAUNCH(k_cdlp_big_scan, (unsigned)p.n_scan, 256, 0, p.listL.p, p.scan_row.p, p.scan_begin.p, p.tab_off.p, act,
-                                  p.gkeys.p, p.gcnt.p, p.best.p);
+                                  p.gtab.p, p.best.p);
                     }
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, act, changed);
                 }
+                if (p.nb[8])
+                    GX_LAUNCH(k_cdlp_cta_rows<8192>, grid_persistent(3), 256, 8192 * 8, p.list[8].p, p.nb[8], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                if (p.nb[7])
+                    GX_LAUNCH(k_cdlp_cta_rows<4096>, grid_persistent(6), 256, 4096 * 8, p.list[7].p, p.nb[7], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                if (p.nb[6])
+                    GX_LAUNCH(k_cdlp_cta_rows<2048>, grid_persistent(8), 256, 2048 * 8, p.list[6].p, p.nb[6], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[5])
-                    GX_LAUNCH(k_cdlp_cta_rows, grid_persistent(3), 256, SMEM_C, p.list[5].p, p.nb[5], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                    GX_LAUNCH(k_cdlp_warp_rows<1024>, grid_persistent(3), 256, 8 * 1024 * 8, p.list[5].p, p.nb[5], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[4])
-                    GX_LAUNCH(k_cdlp_warp_rows, grid_persistent(3), 256, SMEM_M, p.list[4].p, p.nb[4], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                    GX_LAUNCH(k_cdlp_warp_rows<256>, grid_persistent(8), 256, 8 * 256 * 8, p.list[4].p, p.nb[4], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[3]) GX_LAUNCH(k_cdlp_tiny<32>, grid_persistent(8), 256, 0, p.list[3].p, p.nb[3], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[2]) GX_LAUNCH(k_cdlp_tiny<16>, grid_persistent(8), 256, 0, p.list[2].p, p.nb[2], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[1]) GX_LAUNCH(k_cdlp_tiny<8>, grid_persistent(8), 256, 0, p.list[1].p, p.nb[1], rp0, col0, rp1, col1, cur, nxt, act, changed);
