@@ -48,23 +48,24 @@ constexpr uint32_t CDLP_M_MAX = 512, CDLP_C_MAX = 4096;
 constexpr uint32_t CDLP_M1_MAX = 128, CDLP_C1_MAX = 1024, CDLP_C2_MAX = 2048;
 constexpr uint32_t CDLP_PIECE = 4096;  // hub entries per CTA
 constexpr uint32_t CDLP_CT = 8192;     // slots of the CTA-wide shared-memory table (64 KB)
-constexpr uint32_t SCAN_CHUNK = 8192;  // global table slots per CTA in the arg-max pass
+constexpr uint32_t CDLP_EPOCHS = 16, CDLP_CNT_MASK = 0x0FFFFFFFu; // 4-bit epoch tag above a 28-bit count
 
 struct CdlpPlan {
     bool built = false;
     bool first_closed_form = false; // undirected, no repeated entries: iteration 1 is "smallest neighbour"
     Partition part; // row blocks balanced by entries (out + in)
     uint64_t nb[CDLP_BINS] = {0}; // rows per bin
-    uint64_t nL = 0, n_ins = 0, n_scan = 0, slots = 0; // L = hub rows (bin H)
+    uint64_t nL = 0, n_ins = 0, slots = 0; // L = hub rows (bin H)
+    uint32_t epoch = 0;            // of the last iteration that used the hub tables (1 .. CDLP_EPOCHS - 1; 0 = just cleared)
     DevBuf<uint32_t> list[CDLP_BINS - 1], listL;
     DevBuf<uint64_t> tab_off;      // nL + 1: first slot of each L row's table
     DevBuf<uint32_t> ins_row;      // insert chunks: index into listL
     DevBuf<uint8_t> ins_side;      // 0 = out adjacency, 1 = in adjacency
     DevBuf<uint64_t> ins_begin;    // first entry of the chunk
-    DevBuf<uint32_t> scan_row;     // scan chunks: index into listL
-    DevBuf<uint64_t> scan_begin;   // first slot of the chunk
-    DevBuf<uint2> gtab;            // global tables: slot = {label + 1 (0 = empty), count}, one 8-byte word, so that the
-                                   // claim of a slot and the add that follows touch one DRAM sector and one memset clears both
+    DevBuf<uint2> gtab;            // global tables: slot = {label + 1, epoch << 28 | count}, one 8-byte word.  A slot whose
+                                   // epoch is not the running iteration's is free: nothing is cleared between iterations
+                                   // (a memset of 16 bytes per hub entry and, in sparse iterations, a scan of the active
+                                   // rows' tables before); one memset every CDLP_EPOCHS - 1 iterations when the tag wraps
     DevBuf<unsigned long long> best; // nL arg-max accumulators
 };
 
@@ -118,8 +119,9 @@ __global__ void k_cdlp_init(uint32_t *__restrict__ a, uint32_t *__restrict__ b, 
     for (; v < n; v += stride) { a[v] = (uint32_t)v; b[v] = (uint32_t)v; }
 }
 
-// bins T4..T32: G lanes per row, one neighbour label per lane, no table
-template <int G>
+// bins T4..T32: G lanes per row, one neighbour label per lane, no table.  K32 (n <= 2^28): the (group, label) match key
+// fits 32 bits -- MATCH.ANY on a 64-bit key is the dearer instruction, and these kernels are all match + row bookkeeping.
+template <int G, bool K32>
 __global__ void __launch_bounds__(256)
 k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
             const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
@@ -151,9 +153,15 @@ k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *_
             continue;
         }
         // lanes of one row with equal labels match each other; rows (groups) and idle lanes never do
-        const unsigned long long key = have ? (((unsigned long long)(lane_id() / G) << 32) | lab)
-                                            : ((unsigned long long)(0x100u + lane_id()) << 32);
-        const unsigned same = __match_any_sync(FULL, key);
+        unsigned same;
+        if (K32) {
+            // group in bits 29-31, bit 28 clear; idle lanes: bit 28 set + the lane
+            same = __match_any_sync(FULL, have ? (((lane_id() / G) << 29) | lab) : (0x10000000u | lane_id()));
+        } else {
+            const unsigned long long key = have ? (((unsigned long long)(lane_id() / G) << 32) | lab)
+                                                : ((unsigned long long)(0x100u + lane_id()) << 32);
+            same = __match_any_sync(FULL, key);
+        }
         unsigned long long best = have ? (((unsigned long long)__popc(same) << 32) | (uint32_t)~lab) : 0ull;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -276,9 +284,9 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
     if (ch) *changed = 1;
 }
 
-// bins C1 / C2 / C3: one CTA per row, a CT-slot table in shared memory (CT >= 2 x the bin's longest row)
-template <uint32_t CT>
-__global__ void __launch_bounds__(256)
+// bins C1 / C2 / C3: one CTA per row, a CT-slot table in shared memory (CT >= 2 x the bin's longest row), NT threads
+template <uint32_t CT, uint32_t NT>
+__global__ void __launch_bounds__(NT)
 k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
                 const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
                 const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
@@ -286,8 +294,8 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     uint32_t *key = s_tab, *cnt = s_tab + CT;
-    __shared__ unsigned long long s_best[8];
-    for (uint32_t i = threadIdx.x; i < CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
+    __shared__ unsigned long long s_best[NT / 32];
+    for (uint32_t i = threadIdx.x; i < CT; i += NT) { key[i] = EMPTY; cnt[i] = 0; }
     __syncthreads();
     for (uint64_t r = blockIdx.x; r < count; r += gridDim.x) {
         const uint32_t v = list[r];
@@ -299,18 +307,18 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
         while (teff < 2 * d && teff < CT) teff <<= 1;
         const uint32_t mask = teff - 1;
         unsigned long long best = 0;
-        for (uint64_t base = 0; base < d; base += 256 * CDLP_U) {
+        for (uint64_t base = 0; base < d; base += NT * CDLP_U) {
             uint32_t lab[CDLP_U];
-            cdlp_labels(col0, a0, d0, col1, a1, d, base + threadIdx.x, 256, cur, lab);
+            cdlp_labels(col0, a0, d0, col1, a1, d, base + threadIdx.x, NT, cur, lab);
 #pragma unroll
             for (int j = 0; j < CDLP_U; j++)
-                if (base + 256u * j + (threadIdx.x & ~31u) < d) { // warp-uniform
+                if (base + NT * j + (threadIdx.x & ~31u) < d) { // warp-uniform
                     const unsigned long long kk = warp_insert(key, cnt, mask, lab[j], lab[j] != EMPTY);
                     best = kk > best ? kk : best;
                 }
         }
         __syncthreads();
-        smem_table_clear(key, cnt, teff, threadIdx.x, 256);
+        smem_table_clear(key, cnt, teff, threadIdx.x, NT);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long x = __shfl_xor_sync(FULL, best, o);
@@ -320,7 +328,7 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
         __syncthreads();
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int i = 1; i < 8; i++) best = s_best[i] > best ? s_best[i] : best;
+            for (int i = 1; i < (int)(NT / 32); i++) best = s_best[i] > best ? s_best[i] : best;
             const uint32_t nl = ~(uint32_t)best;
             nxt[v] = nl;
             if (nl != cur[v]) *changed = 1;
@@ -331,21 +339,22 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
 
 // hub rows, pass 1: one CTA per CDLP_PIECE entries.  The piece is aggregated in shared memory
 // first; only its distinct labels go to the row's global table (one atomicAdd of the count each).
-__global__ void __launch_bounds__(256)
+constexpr uint32_t CDLP_HT = 512; // threads of a hub-piece CTA (3 CTAs of 64 KB per SM: 48 warps)
+__global__ void __launch_bounds__(CDLP_HT)
 k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict__ ins_row,
                   const uint8_t *__restrict__ ins_side, const uint64_t *__restrict__ ins_begin,
                   const uint64_t *__restrict__ tab_off, const uint64_t *__restrict__ rp0, const uint32_t *__restrict__ col0,
                   const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1, const uint32_t *__restrict__ cur,
-                  const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, unsigned long long *__restrict__ best_out)
+                  const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, uint32_t epoch, unsigned long long *__restrict__ best_out)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
-    __shared__ unsigned long long s_best[8];
+    __shared__ unsigned long long s_best[CDLP_HT / 32];
     const uint32_t c = blockIdx.x;
     const uint32_t li = ins_row[c];
     const uint32_t v = listL[li];
     if (active && !active[v]) return;
-    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += 256) { key[i] = EMPTY; cnt[i] = 0; }
+    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += CDLP_HT) { key[i] = EMPTY; cnt[i] = 0; }
     __syncthreads();
     const bool side = ins_side[c] != 0;
     const uint64_t *rp = side ? rp1 : rp0;
@@ -355,23 +364,23 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
     const uint64_t e_end = (b0 + CDLP_PIECE < row_end) ? b0 + CDLP_PIECE : row_end;
     const uint64_t t0 = tab_off[li];
     const uint64_t tsize = tab_off[li + 1] - t0;
-    for (uint64_t base = b0; base < e_end; base += 256 * CDLP_U) {
+    for (uint64_t base = b0; base < e_end; base += CDLP_HT * CDLP_U) {
         uint32_t lab[CDLP_U];
-        cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, 256, cur, lab);
+        cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, CDLP_HT, cur, lab);
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++)
-            if (base + 256u * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
+            if (base + CDLP_HT * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
     }
     __syncthreads();
     // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
     // the row has seen is the row's arg-max: one atomicMax per piece, and the slot-parallel scan of the table
     // is only needed to clear it (a memset does that when every row is active).
-    // Each warp owns 1/8 of the table.  It first compacts its non-empty slots to the front of its share (in place: the
+    // Each warp owns an equal share of the table.  It first compacts its non-empty slots to the front of its share (in place: the
     // write position never passes the read position), so that every lane of every later trip has work -- with a few
     // hundred distinct labels per piece most trips of the strided walk waited two dependent L2-miss atomics for one or two
     // lanes.  Then the target lines of all its (label, count) pairs are prefetched into L2, and only then come the
     // atomics: CDLP_U claims in flight per lane, then their adds (same 8-byte slot, now an L2 hit).
-    constexpr uint32_t SHARE = CDLP_CT / 8;
+    constexpr uint32_t SHARE = CDLP_CT / (CDLP_HT / 32);
     const unsigned lane = lane_id();
     uint32_t *wkey = key + (threadIdx.x >> 5) * SHARE, *wcnt = cnt + (threadIdx.x >> 5) * SHARE;
     uint32_t nw = 0;
@@ -387,28 +396,49 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
         const uint64_t sl = ((uint64_t)hash32(wkey[i]) * tsize) >> 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gtab + t0 + sl));
     }
+    // Claiming a slot: a slot tagged with this iteration's epoch is live (ours if it holds the label, else probe on);
+    // any other tag means free, and it is claimed by a 64-bit compare-and-swap from the value just seen -- losing that
+    // race makes the slot live, so it is simply looked at again.
+    const uint32_t tag = epoch << 28;
     unsigned long long best = 0;
     for (uint32_t i0 = lane; i0 < nw; i0 += 32 * CDLP_U) {
-        uint32_t cc[CDLP_U], lab[CDLP_U], seen[CDLP_U];
+        uint32_t cc[CDLP_U], lab[CDLP_U];
         uint64_t s[CDLP_U];
+        uint2 seen[CDLP_U];
+        bool claimed[CDLP_U];
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++) {
+            claimed[j] = false;
             const bool have = i0 + 32 * j < nw;
             cc[j] = have ? wcnt[i0 + 32 * j] : 0u;
             lab[j] = have ? wkey[i0 + 32 * j] : EMPTY;
             s[j] = ((uint64_t)hash32(lab[j]) * tsize) >> 32;
         }
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? atomicCAS(&gtab[t0 + s[j]].x, 0u, lab[j] + 1u) - 1u : EMPTY;
+        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? __ldcg(gtab + t0 + s[j]) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++)
-            while (seen[j] != EMPTY && seen[j] != lab[j]) { // (only with cc[j] != 0) the slot belongs to another label
-                s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
-                seen[j] = atomicCAS(&gtab[t0 + s[j]].x, 0u, lab[j] + 1u) - 1u;
+        for (int j = 0; j < CDLP_U; j++) {
+            if (!cc[j]) continue;
+            for (;;) {
+                if ((seen[j].y & ~CDLP_CNT_MASK) == tag) {
+                    if (seen[j].x == lab[j] + 1u) break;
+                    s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
+                    seen[j] = __ldcg(gtab + t0 + s[j]);
+                    continue;
+                }
+                const unsigned long long was = ((unsigned long long)seen[j].y << 32) | seen[j].x;
+                // (the claim carries the piece's count: claiming and the first add are one operation)
+                const unsigned long long want = ((unsigned long long)(tag | cc[j]) << 32) | (lab[j] + 1u);
+                const unsigned long long got = atomicCAS((unsigned long long *)(gtab + t0 + s[j]), was, want);
+                if (got == was) { claimed[j] = true; break; }
+                seen[j] = make_uint2((uint32_t)got, (uint32_t)(got >> 32));
             }
+        }
         unsigned long long now[CDLP_U];
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) now[j] = cc[j] ? (unsigned long long)atomicAdd(&gtab[t0 + s[j]].y, cc[j]) + cc[j] : 0ull;
+        for (int j = 0; j < CDLP_U; j++)
+            now[j] = claimed[j] ? cc[j]
+                   : cc[j]      ? (unsigned long long)((atomicAdd(&gtab[t0 + s[j]].y, cc[j]) + cc[j]) & CDLP_CNT_MASK) : 0ull;
 #pragma unroll
         for (int j = 0; j < CDLP_U; j++) {
             const unsigned long long kk = (now[j] << 32) | (uint32_t)~lab[j];
@@ -424,49 +454,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 1; i < 8; i++) best = s_best[i] > best ? s_best[i] : best;
-        if (best) atomicMax(&best_out[li], best);
-    }
-}
-
-// L rows, pass 2: slot-parallel arg-max, table reset
-__global__ void __launch_bounds__(256)
-k_cdlp_big_scan(const uint32_t *__restrict__ listL, const uint32_t *__restrict__ scan_row,
-                const uint64_t *__restrict__ scan_begin, const uint64_t *__restrict__ tab_off,
-                const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, unsigned long long *__restrict__ best_out)
-{
-    const uint32_t c = blockIdx.x;
-    const uint32_t li = scan_row[c];
-    if (active && !active[listL[li]]) return; // nothing was inserted
-    const uint64_t s0 = scan_begin[c];
-    const uint64_t t_end = tab_off[li + 1];
-    const uint64_t s_end = (s0 + SCAN_CHUNK < t_end) ? s0 + SCAN_CHUNK : t_end;
-    unsigned long long best = 0;
-    for (uint64_t sb = s0 + threadIdx.x; sb < s_end; sb += 256 * 8) {
-        uint2 cc[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { const uint64_t q = sb + (uint64_t)j * 256; cc[j] = q < s_end ? __ldcg(gtab + q) : make_uint2(0u, 0u); }
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (cc[j].x) {
-                const uint64_t q = sb + (uint64_t)j * 256;
-                const unsigned long long kk = ((unsigned long long)cc[j].y << 32) | (uint32_t)~(cc[j].x - 1u);
-                best = kk > best ? kk : best;
-                gtab[q] = make_uint2(0u, 0u);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long x = __shfl_xor_sync(FULL, best, o);
-        best = x > best ? x : best;
-    }
-    __shared__ unsigned long long red[8];
-    if (lane_id() == 0) red[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 1; i < 8; i++) best = red[i] > best ? red[i] : best;
+        for (int i = 1; i < (int)(CDLP_HT / 32); i++) best = s_best[i] > best ? s_best[i] : best;
         if (best) atomicMax(&best_out[li], best);
     }
 }
@@ -644,8 +632,8 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
         std::vector<uint64_t> hx(4 * p->nL);
         GX_CUDA(cudaMemcpyAsync(hx.data(), ext.p, 4 * p->nL * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
         GX_CUDA(cudaStreamSynchronize(s));
-        std::vector<uint64_t> tab_off(p->nL + 1), ins_begin, scan_begin;
-        std::vector<uint32_t> ins_row, scan_row;
+        std::vector<uint64_t> tab_off(p->nL + 1), ins_begin;
+        std::vector<uint32_t> ins_row;
         std::vector<uint8_t> ins_side;
         uint64_t off = 0;
         for (uint64_t i = 0; i < p->nL; i++) {
@@ -656,24 +644,20 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
                 d += b1 - a1;
                 for (uint64_t b = a1; b < b1; b += CDLP_PIECE) { ins_row.push_back((uint32_t)i); ins_side.push_back(1); ins_begin.push_back(b); }
             }
+            GX_REQUIRE(d <= CDLP_CNT_MASK, "CDLP: a row with 2^28 or more entries (the hub tables count in 28 bits)");
             tab_off[i] = off;
-            for (uint64_t sb = off; sb < off + 2 * d; sb += SCAN_CHUNK) { scan_row.push_back((uint32_t)i); scan_begin.push_back(sb); }
             off += 2 * d;
         }
         tab_off[p->nL] = off;
         p->slots = off;
         p->n_ins = ins_row.size();
-        p->n_scan = scan_row.size();
         p->tab_off.alloc(p->nL + 1);
         p->ins_row.alloc(p->n_ins); p->ins_side.alloc(p->n_ins); p->ins_begin.alloc(p->n_ins);
-        p->scan_row.alloc(p->n_scan); p->scan_begin.alloc(p->n_scan);
         p->gtab.alloc(off); p->best.alloc(p->nL);
         GX_CUDA(cudaMemcpyAsync(p->tab_off.p, tab_off.data(), (p->nL + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_row.p, ins_row.data(), p->n_ins * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_side.p, ins_side.data(), p->n_ins * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_begin.p, ins_begin.data(), p->n_ins * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        GX_CUDA(cudaMemcpyAsync(p->scan_row.p, scan_row.data(), p->n_scan * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        GX_CUDA(cudaMemcpyAsync(p->scan_begin.p, scan_begin.data(), p->n_scan * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         p->gtab.zero();
         p->best.zero();
         GX_CUDA(cudaStreamSynchronize(s));
@@ -717,12 +701,13 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
         const uint32_t *col0 = g->out.col.p, *col1 = g->directed ? g->in.col.p : nullptr;
         constexpr size_t SMEM_C = (size_t)CDLP_CT * 8;
         GX_CUDA(cudaFuncSetAttribute(k_cdlp_warp_rows<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8));
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows<CDLP_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows<CDLP_CT, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
         GX_CUDA(cudaFuncSetAttribute(k_cdlp_big_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
         g->res_u64.alloc(n);
         const uint64_t m_eff = g->directed ? 2 * g->m : g->m;
         const char *ae = getenv("GX_CDLP_ACTIVE"); // GX_CDLP_ACTIVE=0: recompute every row every iteration
         const bool use_active = !(ae && ae[0] == '0');
+        const bool k32 = n <= (1ull << 28); // 32-bit match keys in the register kernels
         DevBuf<uint32_t> la(n), lb(n);
         DevBuf<uint8_t> active(use_active ? n : 0);
         DevBuf<unsigned long long> stats(3); // [0] changed flag, [1] entries of the changed rows, [2] entries of marked rows (all sparse iterations)
@@ -744,32 +729,36 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                     inspected += n;
                 } else {
                 if (p.nL) {
-                    GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, 256, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
-                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gtab.p, p.best.p);
-                    if (!act) {
-                        // every hub row was filled: clearing the tables is one memset (the scan costs 5 ms per
-                        // iteration while the labels are still many)
+                    if (++p.epoch == CDLP_EPOCHS) { // the tag wraps: slots of 15 iterations ago would look live again
                         p.gtab.zero();
-                    } else {
-                        GX_LAUNCH(k_cdlp_big_scan, (unsigned)p.n_scan, 256, 0, p.listL.p, p.scan_row.p, p.scan_begin.p, p.tab_off.p, act,
-                                  p.gtab.p, p.best.p);
+                        p.epoch = 1;
                     }
+                    GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, CDLP_HT, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
+                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gtab.p, p.epoch, p.best.p);
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, act, changed);
                 }
                 if (p.nb[8])
-                    GX_LAUNCH(k_cdlp_cta_rows<8192>, grid_persistent(3), 256, 8192 * 8, p.list[8].p, p.nb[8], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                    GX_LAUNCH((k_cdlp_cta_rows<8192, 512>), grid_persistent(3), 512, 8192 * 8, p.list[8].p, p.nb[8], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[7])
-                    GX_LAUNCH(k_cdlp_cta_rows<4096>, grid_persistent(6), 256, 4096 * 8, p.list[7].p, p.nb[7], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                    GX_LAUNCH((k_cdlp_cta_rows<4096, 256>), grid_persistent(6), 256, 4096 * 8, p.list[7].p, p.nb[7], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[6])
-                    GX_LAUNCH(k_cdlp_cta_rows<2048>, grid_persistent(8), 256, 2048 * 8, p.list[6].p, p.nb[6], rp0, col0, rp1, col1, cur, nxt, act, changed);
+                    GX_LAUNCH((k_cdlp_cta_rows<2048, 256>), grid_persistent(8), 256, 2048 * 8, p.list[6].p, p.nb[6], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[5])
                     GX_LAUNCH(k_cdlp_warp_rows<1024>, grid_persistent(3), 256, 8 * 1024 * 8, p.list[5].p, p.nb[5], rp0, col0, rp1, col1, cur, nxt, act, changed);
                 if (p.nb[4])
                     GX_LAUNCH(k_cdlp_warp_rows<256>, grid_persistent(8), 256, 8 * 256 * 8, p.list[4].p, p.nb[4], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[3]) GX_LAUNCH(k_cdlp_tiny<32>, grid_persistent(8), 256, 0, p.list[3].p, p.nb[3], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[2]) GX_LAUNCH(k_cdlp_tiny<16>, grid_persistent(8), 256, 0, p.list[2].p, p.nb[2], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[1]) GX_LAUNCH(k_cdlp_tiny<8>, grid_persistent(8), 256, 0, p.list[1].p, p.nb[1], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[0]) GX_LAUNCH(k_cdlp_tiny<4>, grid_persistent(8), 256, 0, p.list[0].p, p.nb[0], rp0, col0, rp1, col1, cur, nxt, act, changed);
+#define CDLP_TINY(G, b)                                                                                                             \
+    do {                                                                                                                            \
+        if (p.nb[b] && k32)                                                                                                         \
+            GX_LAUNCH((k_cdlp_tiny<G, true>), grid_persistent(8), 256, 0, p.list[b].p, p.nb[b], rp0, col0, rp1, col1, cur, nxt, act, changed);  \
+        else if (p.nb[b])                                                                                                           \
+            GX_LAUNCH((k_cdlp_tiny<G, false>), grid_persistent(8), 256, 0, p.list[b].p, p.nb[b], rp0, col0, rp1, col1, cur, nxt, act, changed); \
+    } while (0)
+                CDLP_TINY(32, 3);
+                CDLP_TINY(16, 2);
+                CDLP_TINY(8, 1);
+                CDLP_TINY(4, 0);
+#undef CDLP_TINY
                 if (!act) inspected += m_eff; else sparse_iters++;
                 }
                 const bool more = it + 1 < itermax;
