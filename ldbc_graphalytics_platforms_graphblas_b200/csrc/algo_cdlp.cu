@@ -10,26 +10,31 @@
 // the scratch is 8 B per slot only for the few rows that spill out of shared
 // memory (the reference allocates 48 B per edge, cdlp_kernel.cu:1169).
 //
-// Rows are binned by entry count d once per graph:
+// Rows are binned by entry count d once per graph; a bin's table is sized for its longest row, so that the shared
+// memory of a CTA -- hence the number of warps an SM keeps in flight -- follows the bin (every row is a chain of
+// dependent misses, offsets -> column ids -> labels, that only other rows can overlap):
 //   T4..T32  d <= 4 / 8 / 16 / 32   G = 4/8/16/32 lanes per row, one label per lane, counted with a
 //                  single __match_any_sync on (group, label) -- registers only, no table
-//   M  d <= 512    warp per row,  1024-slot open-addressing table in shared memory
-//   C  d <= 4096   CTA per row,   8192-slot table in shared memory
-//   H  d  > 4096   (hubs) 4096-entry pieces: a CTA first aggregates its piece in an 8192-slot smem
-//                  table, then adds one (label, count) per DISTINCT label to the row's global
-//                  table of 2d slots; then a slot-parallel arg-max and a per-row finalize
-// Shared-memory atomics cost ~4 cycles per entry per SM, so equal labels met by one warp
-// instruction are merged first (__match_any_sync, leader lane adds the count): once labels
-// converge a row's neighbours share a few labels and most atomics disappear.
-// The arg-max key is (count << 32) | ~label, so max() picks the highest count
-// and, among equals, the smallest label -- bit-exact with the sorted-run scan.
+//   M1 M2    d <= 128 / 512         warp per row, 256- / 1024-slot open-addressing table per warp in shared memory
+//   C1 C2 C3 d <= 1024 / 2048 / 4096  CTA per row, 2048- / 4096- / 8192-slot table in shared memory
+//   H        d  > 4096   (hubs) 4096-entry pieces: a 512-thread CTA aggregates its piece in an 8192-slot smem table,
+//                  compacts the distinct labels, prefetches their slots of the row's global table (2d slots of
+//                  {label + 1, epoch | count}) and then claims / adds; a per-row finalize
+// All table kernels keep CDLP_U (4) column ids and then 4 labels in flight per lane.
+// Shared-memory atomics cost ~2 cycles per lane, so equal labels met by one warp instruction are merged first
+// (__match_any_sync, leader lane adds the count): once labels converge a row's neighbours share a few labels and
+// most atomics disappear.  The arg-max key is (count << 32) | ~label, so max() picks the highest count and, among
+// equals, the smallest label -- bit-exact with the sorted-run scan.  No table is ever scanned: the add that
+// completes a label's count returns the full count, so the largest key any add of a row has returned is the row's
+// arg-max; shared-memory tables are cleared with vector stores, the hub tables are never cleared -- a slot tagged
+// with another iteration's epoch is free.
 // Active rows.  L_{t+1}(v) depends only on L_t of v's neighbours, so a row none of whose neighbours
 // changed in the last iteration keeps its label.  After each iteration k_cdlp_stat adds up the
 // entries of the rows that changed; once that is below 1/8 of all entries the changed rows mark their
-// neighbours in a byte map (k_cdlp_mark_rows, k_cdlp_mark_pieces for the hubs) and
-// the next iteration recomputes only marked rows -- on RMAT graphs iterations 5..10 touch ~5-15 %
-// of the entries.  The labels are the same bit for bit: skipped rows would have recomputed the
-// value they already hold.
+// neighbours in a byte map (k_cdlp_mark_rows, k_cdlp_mark_pieces for the hubs), the marked rows of every bin and
+// the pieces of the marked hubs are compacted (k_cdlp_compact_active) and the next iteration recomputes only those
+// -- on RMAT graphs iterations 5..10 touch ~5-15 % of the entries.  The labels are the same bit for bit: skipped
+// rows would have recomputed the value they already hold.
 // Algorithmic bytes per iteration: 4 m' + 8(n+1) [x2 directed] + 4n + 4n.
 #include <algorithm>
 #include <cstdlib>
@@ -67,6 +72,9 @@ struct CdlpPlan {
                                    // (a memset of 16 bytes per hub entry and, in sparse iterations, a scan of the active
                                    // rows' tables before); one memset every CDLP_EPOCHS - 1 iterations when the tag wraps
     DevBuf<unsigned long long> best; // nL arg-max accumulators
+    // sparse iterations: the active rows of every bin and the pieces of the active hub rows, compacted per iteration
+    DevBuf<uint32_t> alist[CDLP_BINS - 1], apieces;
+    DevBuf<unsigned long long> acount; // CDLP_BINS counters (the last one: pieces)
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t h)
@@ -123,13 +131,15 @@ __global__ void k_cdlp_init(uint32_t *__restrict__ a, uint32_t *__restrict__ b, 
 // fits 32 bits -- MATCH.ANY on a 64-bit key is the dearer instruction, and these kernels are all match + row bookkeeping.
 template <int G, bool K32>
 __global__ void __launch_bounds__(256)
-k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+k_cdlp_tiny(const uint32_t *__restrict__ list, uint64_t count, const unsigned long long *__restrict__ count_dev,
+            const uint64_t *__restrict__ rp0,
             const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
             const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
             int *__restrict__ changed)
 {
     const unsigned sub = threadIdx.x & (G - 1);
     uint64_t gi = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / G;
+    if (count_dev) count = *count_dev; // sparse iterations: `list` holds the active rows only, counted on the device
     const uint64_t ngrp = ((uint64_t)gridDim.x * 256) / G;
     const uint64_t trips = (count + ngrp - 1) / ngrp; // same for every lane: the warp-wide intrinsics stay convergent
     bool ch = false;
@@ -234,7 +244,8 @@ __device__ __forceinline__ void cdlp_labels(const uint32_t *__restrict__ col0, u
 // bins M1 / M2: one warp per row, a WT-slot table per warp in shared memory (WT >= 2 x the bin's longest row)
 template <uint32_t CDLP_WT>
 __global__ void __launch_bounds__(256)
-k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const unsigned long long *__restrict__ count_dev,
+                 const uint64_t *__restrict__ rp0,
                  const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
                  const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
                  int *__restrict__ changed)
@@ -245,6 +256,7 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
     uint32_t *key = s_tab + wib * CDLP_WT;
     uint32_t *cnt = s_tab + 8 * CDLP_WT + wib * CDLP_WT;
+    if (count_dev) count = *count_dev;
     const uint64_t nwarp = (uint64_t)gridDim.x * 8;
     bool ch = false;
     for (uint64_t r = (uint64_t)blockIdx.x * 8 + wib; r < count; r += nwarp) {
@@ -287,7 +299,8 @@ k_cdlp_warp_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64
 // bins C1 / C2 / C3: one CTA per row, a CT-slot table in shared memory (CT >= 2 x the bin's longest row), NT threads
 template <uint32_t CT, uint32_t NT>
 __global__ void __launch_bounds__(NT)
-k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_t *__restrict__ rp0,
+k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const unsigned long long *__restrict__ count_dev,
+                const uint64_t *__restrict__ rp0,
                 const uint32_t *__restrict__ col0, const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1,
                 const uint32_t *__restrict__ cur, uint32_t *__restrict__ nxt, const uint8_t *__restrict__ active,
                 int *__restrict__ changed)
@@ -297,6 +310,7 @@ k_cdlp_cta_rows(const uint32_t *__restrict__ list, uint64_t count, const uint64_
     __shared__ unsigned long long s_best[NT / 32];
     for (uint32_t i = threadIdx.x; i < CT; i += NT) { key[i] = EMPTY; cnt[i] = 0; }
     __syncthreads();
+    if (count_dev) count = *count_dev;
     for (uint64_t r = blockIdx.x; r < count; r += gridDim.x) {
         const uint32_t v = list[r];
         if (active && !active[v]) { if (threadIdx.x == 0) nxt[v] = cur[v]; continue; } // uniform per CTA
@@ -345,117 +359,122 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
                   const uint8_t *__restrict__ ins_side, const uint64_t *__restrict__ ins_begin,
                   const uint64_t *__restrict__ tab_off, const uint64_t *__restrict__ rp0, const uint32_t *__restrict__ col0,
                   const uint64_t *__restrict__ rp1, const uint32_t *__restrict__ col1, const uint32_t *__restrict__ cur,
-                  const uint8_t *__restrict__ active, uint2 *__restrict__ gtab, uint32_t epoch, unsigned long long *__restrict__ best_out)
+                  const uint32_t *__restrict__ piece_ids, const unsigned long long *__restrict__ npieces_dev, uint32_t npieces,
+                  uint2 *__restrict__ gtab, uint32_t epoch, unsigned long long *__restrict__ best_out)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
     uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
     __shared__ unsigned long long s_best[CDLP_HT / 32];
-    const uint32_t c = blockIdx.x;
-    const uint32_t li = ins_row[c];
-    const uint32_t v = listL[li];
-    if (active && !active[v]) return;
-    for (uint32_t i = threadIdx.x; i < CDLP_CT; i += CDLP_HT) { key[i] = EMPTY; cnt[i] = 0; }
-    __syncthreads();
-    const bool side = ins_side[c] != 0;
-    const uint64_t *rp = side ? rp1 : rp0;
-    const uint32_t *col = side ? col1 : col0;
-    const uint64_t b0 = ins_begin[c];
-    const uint64_t row_end = rp[v + 1];
-    const uint64_t e_end = (b0 + CDLP_PIECE < row_end) ? b0 + CDLP_PIECE : row_end;
-    const uint64_t t0 = tab_off[li];
-    const uint64_t tsize = tab_off[li + 1] - t0;
-    for (uint64_t base = b0; base < e_end; base += CDLP_HT * CDLP_U) {
-        uint32_t lab[CDLP_U];
-        cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, CDLP_HT, cur, lab);
+    // dense iterations: one CTA per piece (piece_ids == NULL); sparse ones: the pieces of the active hub rows, listed and
+    // counted on the device, drawn by a persistent grid
+    if (npieces_dev) npieces = (uint32_t)*npieces_dev;
+    for (uint32_t ci = blockIdx.x; ci < npieces; ci += gridDim.x) {
+        const uint32_t c = piece_ids ? piece_ids[ci] : ci;
+        const uint32_t li = ins_row[c];
+        const uint32_t v = listL[li];
+        for (uint32_t i = threadIdx.x; i < CDLP_CT; i += CDLP_HT) { key[i] = EMPTY; cnt[i] = 0; }
+        __syncthreads();
+        const bool side = ins_side[c] != 0;
+        const uint64_t *rp = side ? rp1 : rp0;
+        const uint32_t *col = side ? col1 : col0;
+        const uint64_t b0 = ins_begin[c];
+        const uint64_t row_end = rp[v + 1];
+        const uint64_t e_end = (b0 + CDLP_PIECE < row_end) ? b0 + CDLP_PIECE : row_end;
+        const uint64_t t0 = tab_off[li];
+        const uint64_t tsize = tab_off[li + 1] - t0;
+        for (uint64_t base = b0; base < e_end; base += CDLP_HT * CDLP_U) {
+            uint32_t lab[CDLP_U];
+            cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, CDLP_HT, cur, lab);
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++)
-            if (base + CDLP_HT * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
-    }
-    __syncthreads();
-    // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
-    // the row has seen is the row's arg-max: one atomicMax per piece, and the slot-parallel scan of the table
-    // is only needed to clear it (a memset does that when every row is active).
-    // Each warp owns an equal share of the table.  It first compacts its non-empty slots to the front of its share (in place: the
-    // write position never passes the read position), so that every lane of every later trip has work -- with a few
-    // hundred distinct labels per piece most trips of the strided walk waited two dependent L2-miss atomics for one or two
-    // lanes.  Then the target lines of all its (label, count) pairs are prefetched into L2, and only then come the
-    // atomics: CDLP_U claims in flight per lane, then their adds (same 8-byte slot, now an L2 hit).
-    constexpr uint32_t SHARE = CDLP_CT / (CDLP_HT / 32);
-    const unsigned lane = lane_id();
-    uint32_t *wkey = key + (threadIdx.x >> 5) * SHARE, *wcnt = cnt + (threadIdx.x >> 5) * SHARE;
-    uint32_t nw = 0;
-    for (uint32_t i = lane; i < SHARE; i += 32) {
-        const uint32_t cc = wcnt[i], lab = wkey[i];
-        const unsigned m = __ballot_sync(FULL, cc != 0);
-        __syncwarp();
-        if (cc) { const uint32_t d = nw + __popc(m & ((1u << lane) - 1u)); wkey[d] = lab; wcnt[d] = cc; }
-        nw += __popc(m);
-        __syncwarp();
-    }
-    for (uint32_t i = lane; i < nw; i += 32) {
-        const uint64_t sl = ((uint64_t)hash32(wkey[i]) * tsize) >> 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(gtab + t0 + sl));
-    }
-    // Claiming a slot: a slot tagged with this iteration's epoch is live (ours if it holds the label, else probe on);
-    // any other tag means free, and it is claimed by a 64-bit compare-and-swap from the value just seen -- losing that
-    // race makes the slot live, so it is simply looked at again.
-    const uint32_t tag = epoch << 28;
-    unsigned long long best = 0;
-    for (uint32_t i0 = lane; i0 < nw; i0 += 32 * CDLP_U) {
-        uint32_t cc[CDLP_U], lab[CDLP_U];
-        uint64_t s[CDLP_U];
-        uint2 seen[CDLP_U];
-        bool claimed[CDLP_U];
-#pragma unroll
-        for (int j = 0; j < CDLP_U; j++) {
-            claimed[j] = false;
-            const bool have = i0 + 32 * j < nw;
-            cc[j] = have ? wcnt[i0 + 32 * j] : 0u;
-            lab[j] = have ? wkey[i0 + 32 * j] : EMPTY;
-            s[j] = ((uint64_t)hash32(lab[j]) * tsize) >> 32;
+            for (int j = 0; j < CDLP_U; j++)
+                if (base + CDLP_HT * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
         }
+        __syncthreads();
+        // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
+        // the row has seen is the row's arg-max: one atomicMax per piece, no scan of the row's table.
+        // Each warp owns an equal share of the table.  It first compacts its non-empty slots to the front of its share (in place: the
+        // write position never passes the read position), so that every lane of every later trip has work -- with a few
+        // hundred distinct labels per piece most trips of the strided walk waited two dependent L2-miss atomics for one or two
+        // lanes.  Then the target lines of all its (label, count) pairs are prefetched into L2, and only then come the
+        // atomics: CDLP_U claims in flight per lane, then their adds (same 8-byte slot, now an L2 hit).
+        constexpr uint32_t SHARE = CDLP_CT / (CDLP_HT / 32);
+        const unsigned lane = lane_id();
+        uint32_t *wkey = key + (threadIdx.x >> 5) * SHARE, *wcnt = cnt + (threadIdx.x >> 5) * SHARE;
+        uint32_t nw = 0;
+        for (uint32_t i = lane; i < SHARE; i += 32) {
+            const uint32_t cc = wcnt[i], lab = wkey[i];
+            const unsigned m = __ballot_sync(FULL, cc != 0);
+            __syncwarp();
+            if (cc) { const uint32_t d = nw + __popc(m & ((1u << lane) - 1u)); wkey[d] = lab; wcnt[d] = cc; }
+            nw += __popc(m);
+            __syncwarp();
+        }
+        for (uint32_t i = lane; i < nw; i += 32) {
+            const uint64_t sl = ((uint64_t)hash32(wkey[i]) * tsize) >> 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gtab + t0 + sl));
+        }
+        // Claiming a slot: a slot tagged with this iteration's epoch is live (ours if it holds the label, else probe on);
+        // any other tag means free, and it is claimed by a 64-bit compare-and-swap from the value just seen -- losing that
+        // race makes the slot live, so it is simply looked at again.
+        const uint32_t tag = epoch << 28;
+        unsigned long long best = 0;
+        for (uint32_t i0 = lane; i0 < nw; i0 += 32 * CDLP_U) {
+            uint32_t cc[CDLP_U], lab[CDLP_U];
+            uint64_t s[CDLP_U];
+            uint2 seen[CDLP_U];
+            bool claimed[CDLP_U];
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? __ldcg(gtab + t0 + s[j]) : make_uint2(0u, 0u);
+            for (int j = 0; j < CDLP_U; j++) {
+                claimed[j] = false;
+                const bool have = i0 + 32 * j < nw;
+                cc[j] = have ? wcnt[i0 + 32 * j] : 0u;
+                lab[j] = have ? wkey[i0 + 32 * j] : EMPTY;
+                s[j] = ((uint64_t)hash32(lab[j]) * tsize) >> 32;
+            }
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++) {
-            if (!cc[j]) continue;
-            for (;;) {
-                if ((seen[j].y & ~CDLP_CNT_MASK) == tag) {
-                    if (seen[j].x == lab[j] + 1u) break;
-                    s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
-                    seen[j] = __ldcg(gtab + t0 + s[j]);
-                    continue;
+            for (int j = 0; j < CDLP_U; j++) seen[j] = cc[j] ? __ldcg(gtab + t0 + s[j]) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int j = 0; j < CDLP_U; j++) {
+                if (!cc[j]) continue;
+                for (;;) {
+                    if ((seen[j].y & ~CDLP_CNT_MASK) == tag) {
+                        if (seen[j].x == lab[j] + 1u) break;
+                        s[j] = (s[j] + 1 == tsize) ? 0 : s[j] + 1;
+                        seen[j] = __ldcg(gtab + t0 + s[j]);
+                        continue;
+                    }
+                    const unsigned long long was = ((unsigned long long)seen[j].y << 32) | seen[j].x;
+                    // (the claim carries the piece's count: claiming and the first add are one operation)
+                    const unsigned long long want = ((unsigned long long)(tag | cc[j]) << 32) | (lab[j] + 1u);
+                    const unsigned long long got = atomicCAS((unsigned long long *)(gtab + t0 + s[j]), was, want);
+                    if (got == was) { claimed[j] = true; break; }
+                    seen[j] = make_uint2((uint32_t)got, (uint32_t)(got >> 32));
                 }
-                const unsigned long long was = ((unsigned long long)seen[j].y << 32) | seen[j].x;
-                // (the claim carries the piece's count: claiming and the first add are one operation)
-                const unsigned long long want = ((unsigned long long)(tag | cc[j]) << 32) | (lab[j] + 1u);
-                const unsigned long long got = atomicCAS((unsigned long long *)(gtab + t0 + s[j]), was, want);
-                if (got == was) { claimed[j] = true; break; }
-                seen[j] = make_uint2((uint32_t)got, (uint32_t)(got >> 32));
+            }
+            unsigned long long now[CDLP_U];
+#pragma unroll
+            for (int j = 0; j < CDLP_U; j++)
+                now[j] = claimed[j] ? cc[j]
+                       : cc[j]      ? (unsigned long long)((atomicAdd(&gtab[t0 + s[j]].y, cc[j]) + cc[j]) & CDLP_CNT_MASK) : 0ull;
+#pragma unroll
+            for (int j = 0; j < CDLP_U; j++) {
+                const unsigned long long kk = (now[j] << 32) | (uint32_t)~lab[j];
+                if (cc[j] && kk > best) best = kk;
             }
         }
-        unsigned long long now[CDLP_U];
 #pragma unroll
-        for (int j = 0; j < CDLP_U; j++)
-            now[j] = claimed[j] ? cc[j]
-                   : cc[j]      ? (unsigned long long)((atomicAdd(&gtab[t0 + s[j]].y, cc[j]) + cc[j]) & CDLP_CNT_MASK) : 0ull;
-#pragma unroll
-        for (int j = 0; j < CDLP_U; j++) {
-            const unsigned long long kk = (now[j] << 32) | (uint32_t)~lab[j];
-            if (cc[j] && kk > best) best = kk;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(FULL, best, o);
+            best = x > best ? x : best;
         }
-    }
+        if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long x = __shfl_xor_sync(FULL, best, o);
-        best = x > best ? x : best;
-    }
-    if (lane_id() == 0) s_best[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 1; i < (int)(CDLP_HT / 32); i++) best = s_best[i] > best ? s_best[i] : best;
-        if (best) atomicMax(&best_out[li], best);
+            for (int i = 1; i < (int)(CDLP_HT / 32); i++) best = s_best[i] > best ? s_best[i] : best;
+            if (best) atomicMax(&best_out[li], best);
+        }
+        __syncthreads(); // the table and s_best are reused by the next piece
     }
 }
 
@@ -511,6 +530,47 @@ __global__ void k_cdlp_first(const uint64_t *__restrict__ rowptr, const uint32_t
 }
 
 // ---- active rows -------------------------------------------------------------------------------
+// Sparse iterations recompute 5 % of the rows: walking every bin's whole list for them (two dependent loads per row,
+// list entry -> active byte) cost more than the rows themselves, and the hub kernel launched 35 K CTAs to find a few
+// active pieces.  The active rows of every bin (blockIdx.y < CDLP_BINS - 1) and the pieces of the active hub rows
+// (blockIdx.y == CDLP_BINS - 1) are compacted first; order inside a 256-row block is kept, blocks land in any order.
+struct CdlpCompact {
+    const uint32_t *src[CDLP_BINS]; // bin lists; the last entry is unused (pieces are numbered 0 .. n - 1)
+    uint32_t *dst[CDLP_BINS];
+    uint64_t n[CDLP_BINS];
+};
+__global__ void __launch_bounds__(256)
+k_cdlp_compact_active(CdlpCompact a, const uint32_t *__restrict__ listL, const uint32_t *__restrict__ ins_row,
+                      const uint8_t *__restrict__ active, unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned long long s_base;
+    const int b = blockIdx.y;
+    const uint64_t n = a.n[b], nround = (n + 255) & ~255ull;
+    const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
+    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < nround; base += (uint64_t)gridDim.x * 256) {
+        const uint64_t i = base + threadIdx.x;
+        uint32_t item = 0;
+        bool in = false;
+        if (i < n) {
+            item = b == CDLP_BINS - 1 ? (uint32_t)i : a.src[b][i];
+            in = active[b == CDLP_BINS - 1 ? listL[ins_row[i]] : item] != 0;
+        }
+        const unsigned mask = __ballot_sync(FULL, in);
+        if (lane == 0) s_cnt[wib] = __popc(mask);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(&counts[b], (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (in) a.dst[b][s_base + s_cnt[wib] + __popc(mask & ((1u << lane) - 1u))] = item;
+        __syncthreads();
+    }
+}
+
 // entries of the rows [v0, v1) whose label just changed (what marking their neighbours would cost)
 __global__ void __launch_bounds__(256)
 k_cdlp_stat(const uint64_t *__restrict__ rp0, const uint64_t *__restrict__ rp1, uint64_t v0, uint64_t v1,
@@ -615,7 +675,8 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
     read_back(h, counts.p, sizeof(h));
     for (int b = 0; b < CDLP_BINS; b++) p->nb[b] = h[b];
     p->nL = h[CDLP_BINS - 1];
-    for (int b = 0; b < CDLP_BINS - 1; b++) { p->list[b].alloc(h[b] ? h[b] : 1); lists.l[b] = p->list[b].p; }
+    for (int b = 0; b < CDLP_BINS - 1; b++) { p->list[b].alloc(h[b] ? h[b] : 1); lists.l[b] = p->list[b].p; p->alist[b].alloc(h[b] ? h[b] : 1); }
+    p->acount.alloc(CDLP_BINS);
     p->listL.alloc(p->nL ? p->nL : 1);
     lists.l[CDLP_BINS - 1] = p->listL.p;
     counts.zero();
@@ -653,7 +714,7 @@ static CdlpPlan *build_cdlp_plan(gx_graph *g)
         p->n_ins = ins_row.size();
         p->tab_off.alloc(p->nL + 1);
         p->ins_row.alloc(p->n_ins); p->ins_side.alloc(p->n_ins); p->ins_begin.alloc(p->n_ins);
-        p->gtab.alloc(off); p->best.alloc(p->nL);
+        p->gtab.alloc(off); p->best.alloc(p->nL); p->apieces.alloc(p->n_ins);
         GX_CUDA(cudaMemcpyAsync(p->tab_off.p, tab_off.data(), (p->nL + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_row.p, ins_row.data(), p->n_ins * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         GX_CUDA(cudaMemcpyAsync(p->ins_side.p, ins_side.data(), p->n_ins * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
@@ -728,37 +789,56 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                     GX_LAUNCH(k_cdlp_first, grid_persistent(8), 256, 0, rp0, col0, p.part.lo, p.part.hi, nxt, changed);
                     inspected += n;
                 } else {
+                // sparse iteration: only the marked rows are recomputed -- they are compacted per bin first (counts stay
+                // on the device), every other row keeps its label by one copy of the label array
+                const bool sparse = act != nullptr;
+                const uint32_t *lst[CDLP_BINS - 1];
+                const unsigned long long *cnt_dev[CDLP_BINS - 1];
+                for (int b = 0; b < CDLP_BINS - 1; b++) { lst[b] = p.list[b].p; cnt_dev[b] = nullptr; }
+                if (sparse) {
+                    CdlpCompact ca{};
+                    for (int b = 0; b < CDLP_BINS - 1; b++) {
+                        ca.src[b] = p.list[b].p; ca.dst[b] = p.alist[b].p; ca.n[b] = p.nb[b];
+                        lst[b] = p.alist[b].p; cnt_dev[b] = p.acount.p + b;
+                    }
+                    ca.src[CDLP_BINS - 1] = nullptr; ca.dst[CDLP_BINS - 1] = p.apieces.p; ca.n[CDLP_BINS - 1] = p.nL ? p.n_ins : 0;
+                    p.acount.zero();
+                    GX_LAUNCH(k_cdlp_compact_active, dim3(2 * (unsigned)c.num_sms, CDLP_BINS), 256, 0, ca, p.listL.p, p.ins_row.p, act, p.acount.p);
+                    GX_CUDA(cudaMemcpyAsync(nxt, cur, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+                }
+                const uint8_t *no_map = nullptr; // the row kernels get compact lists, not the map
                 if (p.nL) {
                     if (++p.epoch == CDLP_EPOCHS) { // the tag wraps: slots of 15 iterations ago would look live again
                         p.gtab.zero();
                         p.epoch = 1;
                     }
-                    GX_LAUNCH(k_cdlp_big_insert, (unsigned)p.n_ins, CDLP_HT, SMEM_C, p.listL.p, p.ins_row.p, p.ins_side.p, p.ins_begin.p,
-                              p.tab_off.p, rp0, col0, rp1, col1, cur, act, p.gtab.p, p.epoch, p.best.p);
+                    GX_LAUNCH(k_cdlp_big_insert, sparse ? grid_persistent(3) : (unsigned)p.n_ins, CDLP_HT, SMEM_C, p.listL.p, p.ins_row.p,
+                              p.ins_side.p, p.ins_begin.p, p.tab_off.p, rp0, col0, rp1, col1, cur, sparse ? p.apieces.p : nullptr,
+                              sparse ? p.acount.p + (CDLP_BINS - 1) : nullptr, (uint32_t)p.n_ins, p.gtab.p, p.epoch, p.best.p);
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, act, changed);
                 }
-                if (p.nb[8])
-                    GX_LAUNCH((k_cdlp_cta_rows<8192, 512>), grid_persistent(3), 512, 8192 * 8, p.list[8].p, p.nb[8], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[7])
-                    GX_LAUNCH((k_cdlp_cta_rows<4096, 256>), grid_persistent(6), 256, 4096 * 8, p.list[7].p, p.nb[7], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[6])
-                    GX_LAUNCH((k_cdlp_cta_rows<2048, 256>), grid_persistent(8), 256, 2048 * 8, p.list[6].p, p.nb[6], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[5])
-                    GX_LAUNCH(k_cdlp_warp_rows<1024>, grid_persistent(3), 256, 8 * 1024 * 8, p.list[5].p, p.nb[5], rp0, col0, rp1, col1, cur, nxt, act, changed);
-                if (p.nb[4])
-                    GX_LAUNCH(k_cdlp_warp_rows<256>, grid_persistent(8), 256, 8 * 256 * 8, p.list[4].p, p.nb[4], rp0, col0, rp1, col1, cur, nxt, act, changed);
-#define CDLP_TINY(G, b)                                                                                                             \
+#define CDLP_ROWS(kern, b, ctas, threads, smem)                                                                                     \
     do {                                                                                                                            \
-        if (p.nb[b] && k32)                                                                                                         \
-            GX_LAUNCH((k_cdlp_tiny<G, true>), grid_persistent(8), 256, 0, p.list[b].p, p.nb[b], rp0, col0, rp1, col1, cur, nxt, act, changed);  \
-        else if (p.nb[b])                                                                                                           \
-            GX_LAUNCH((k_cdlp_tiny<G, false>), grid_persistent(8), 256, 0, p.list[b].p, p.nb[b], rp0, col0, rp1, col1, cur, nxt, act, changed); \
+        if (p.nb[b])                                                                                                                \
+            GX_LAUNCH(kern, grid_persistent(ctas), threads, smem, lst[b], p.nb[b], cnt_dev[b], rp0, col0, rp1, col1, cur, nxt, no_map, changed); \
     } while (0)
-                CDLP_TINY(32, 3);
-                CDLP_TINY(16, 2);
-                CDLP_TINY(8, 1);
-                CDLP_TINY(4, 0);
-#undef CDLP_TINY
+                CDLP_ROWS((k_cdlp_cta_rows<8192, 512>), 8, 3, 512, 8192 * 8);
+                CDLP_ROWS((k_cdlp_cta_rows<4096, 256>), 7, 6, 256, 4096 * 8);
+                CDLP_ROWS((k_cdlp_cta_rows<2048, 256>), 6, 8, 256, 2048 * 8);
+                CDLP_ROWS(k_cdlp_warp_rows<1024>, 5, 3, 256, 8 * 1024 * 8);
+                CDLP_ROWS(k_cdlp_warp_rows<256>, 4, 8, 256, 8 * 256 * 8);
+                if (k32) {
+                    CDLP_ROWS((k_cdlp_tiny<32, true>), 3, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<16, true>), 2, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<8, true>), 1, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<4, true>), 0, 8, 256, 0);
+                } else {
+                    CDLP_ROWS((k_cdlp_tiny<32, false>), 3, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<16, false>), 2, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<8, false>), 1, 8, 256, 0);
+                    CDLP_ROWS((k_cdlp_tiny<4, false>), 0, 8, 256, 0);
+                }
+#undef CDLP_ROWS
                 if (!act) inspected += m_eff; else sparse_iters++;
                 }
                 const bool more = it + 1 < itermax;
