@@ -191,6 +191,33 @@ def test_cdlp_active_rows_match_full_recompute(capi, directed, monkeypatch):
         g.free()
 
 
+@pytest.mark.parametrize("directed", [True, False])
+def test_cdlp_hub_tables_across_many_iterations(capi, directed, monkeypatch):
+    """Hub rows (> 4096 entries) count their labels in global tables whose slots carry a 4-bit epoch tag instead of being
+    cleared (algo_cdlp.cu): 60 iterations on one plan wrap the tag several times, with dense iterations (every piece
+    inserts), sparse ones (only the pieces of marked hubs, drawn from the compacted list) and full recomputes mixed.
+    Three hubs of different sizes, one of them reached through the in-adjacency only."""
+    n = 40000
+    rng = np.random.default_rng(77)
+    e_s, e_d = [], []
+    for hub, deg in ((0, 21000), (1, 9000), (2, 4300)):
+        other = rng.choice(np.arange(3, n), deg, replace=False)
+        if hub == 1:
+            e_s.append(other); e_d.append(np.full(deg, hub))      # in-entries only (directed case)
+        else:
+            e_s.append(np.full(deg, hub)); e_d.append(other)
+    e_s.append(rng.integers(0, n, 120000)); e_d.append(rng.integers(0, n, 120000))
+    hg = csr_from_edges(n, np.concatenate(e_s), np.concatenate(e_d), None, directed)
+    g = capi.Graph.from_host(hg)
+    try:
+        for iters, active in ((10, "1"), (3, "1"), (17, "0"), (9, "1"), (2, "0"), (19, "1")):
+            monkeypatch.setenv("GX_CDLP_ACTIVE", active)
+            ref = oracle.cdlp(hg.n, hg.rowptr, hg.colidx, directed, iters)
+            assert np.array_equal(g.cdlp(iters), ref), (iters, active)
+    finally:
+        g.free()
+
+
 def test_cdlp_first_iteration_closed_form_and_repeated_entries(capi, monkeypatch):
     """Undirected graphs take iteration 1 in closed form (label = smallest neighbour) unless a row
     repeats an entry; a multigraph (dedupe=False) must fall back to counting.  Both against the
