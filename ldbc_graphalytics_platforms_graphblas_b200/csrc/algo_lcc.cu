@@ -36,18 +36,26 @@ constexpr uint32_t LCC_SMEM_SLOTS = 8192; // membership tables up to this many s
 // table and are searched.  Adds the corner counts of the common neighbours, returns this lane's share for u and v.
 template <bool TAB_SMEM, int UNROLL, int LCC_G>
 __device__ __forceinline__ void lcc_intersect(const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ tab, const uint32_t *s_tab,
-                                              uint64_t sa, uint64_t sb, uint64_t la, uint64_t lb, uint64_t t0, uint64_t tmask,
+                                              uint64_t sa, uint64_t sb, uint64_t la, uint64_t lb, uint64_t t0, uint64_t tmask64,
                                               unsigned sub, bool u_short, unsigned long long m_uv, unsigned long long *__restrict__ num,
                                               unsigned long long &su, unsigned long long &sv, int diag)
 {
+    // Index arithmetic in 32 bits relative to the lists' first entries (an oriented row has fewer than 2^31 entries,
+    // a table fewer than 2^32 slots), counts in 32 bits (at most one per walked element): the walk issued at 63 % of
+    // the SM's slots, a good part of it 64-bit compares, selects and adds.
+    const uint32_t *__restrict__ sl_p = ocol + sa; // the walked (shorter) list
+    const uint32_t slen = (uint32_t)(sb - sa);
+    const uint32_t tmask = (uint32_t)tmask64;       // table size (power of two) or 0
+    const uint32_t *__restrict__ tb = tab + t0;
+    uint32_t c_long = 0, c_short = 0; // multiplicities met on the side of the long / the short list's owner
     // UNROLL elements of the shorter list are requested before the first one is looked up: the walk is a chain of
     // dependent L2 / DRAM latencies otherwise (one load in flight per lane)
-    for (uint64_t i = sa + sub; i < sb; i += LCC_G * UNROLL) {
+    for (uint32_t i = sub; i < slen; i += LCC_G * UNROLL) {
         uint32_t cs_[UNROLL];
 #pragma unroll
         for (int j = 0; j < UNROLL; j++) {
-            const uint64_t k = i + (uint64_t)j * LCC_G;
-            cs_[j] = k < sb ? ocol[k] : 0xFFFFFFFFu; // (no entry has this value: ids are < 2^31 - 1)
+            const uint32_t k = i + (uint32_t)j * LCC_G;
+            cs_[j] = k < slen ? sl_p[k] : 0xFFFFFFFFu; // (no entry has this value: ids are < 2^31 - 1)
         }
 #pragma unroll
         for (int j = 0; j < UNROLL; j++) {
@@ -57,9 +65,9 @@ __device__ __forceinline__ void lcc_intersect(const uint32_t *__restrict__ ocol,
             uint32_t cl = 0xFFFFFFFFu; // the longer list's entry for w, if any
             if (tmask) {
                 // open addressing at load 1/4: a miss ends after 1.4 probes on average, all in one line
-                uint64_t sl = lcc_tab_hash(w, tmask);
+                uint32_t sl = (uint32_t)lcc_tab_hash(w, tmask64);
                 for (;;) {
-                    const uint32_t c = TAB_SMEM ? s_tab[sl] : tab[t0 + sl];
+                    const uint32_t c = TAB_SMEM ? s_tab[sl] : tb[sl];
                     if (c == 0xFFFFFFFFu || (c & IDMASK) == w) { cl = c; break; }
                     sl = (sl + 1) & (tmask - 1);
                 }
@@ -72,19 +80,19 @@ __device__ __forceinline__ void lcc_intersect(const uint32_t *__restrict__ ocol,
                 if (lo < lb) cl = ocol[lo];
             }
             if (cl != 0xFFFFFFFFu && (cl & IDMASK) == w) {
-                const unsigned long long m_s = (cs & LCC_MULT_BIT) ? 2ull : 1ull; // side (short owner, w)
-                const unsigned long long m_l = (cl & LCC_MULT_BIT) ? 2ull : 1ull; // side (long owner, w)
-                // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v)
-                su += u_short ? m_l : m_s;
-                sv += u_short ? m_s : m_l;
+                // corner u gets mult(v,w), corner v gets mult(u,w), corner w gets mult(u,v); a multiplicity is 1 or 2
+                c_short += 1u + (cs >> 31); // side (short owner, w)
+                c_long += 1u + (cl >> 31);  // side (long owner, w)
                 if (!diag) atomicAdd(&num[w], m_uv); // diag (GX_LCC_VAR=1): timing diagnostic, results are wrong
             }
         }
     }
+    su += u_short ? c_long : c_short;
+    sv += u_short ? c_short : c_long;
 }
 
 template <int UNROLL, int LCC_G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6) // 6 CTAs of 32 KB + 256 threads per SM: 48 warps, <= 40 registers
 k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol, const uint32_t *__restrict__ eu,
             const uint32_t *__restrict__ ev, const uint32_t *__restrict__ eowner, const uint64_t *__restrict__ tab_off,
             const uint32_t *__restrict__ tab, uint64_t e0, uint64_t om, uint32_t run, unsigned long long *__restrict__ next_run,
