@@ -431,8 +431,10 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(scale, n, m, world),
         "partition": "single GPU" if world == 1 else
-                     f"adjacency replicated, rows split into {world} nnz-balanced blocks, per-vertex state "
-                     "all-gathered / reduced over NVLink every level / iteration",
+                     f"rows split into {world} nnz-balanced blocks (a rank computes its block); out-adjacency on every rank, "
+                     "in-adjacency row-partitioned (block-local transposition); PageRank vector: a rank keeps its own slots "
+                     "plus the sources its rows gather from (3+ ranks) and receives them by peer stores over NVLink, sink "
+                     "mass summed through peer mailboxes; BFS frontier words by one all-reduce per level",
         "per_algorithm": {
             "bfs": {"evps": ev / (kb / args.steps * 1e-3), "kernel_ms": kb / args.steps, "levels": bfs_levels,
                     "edges_inspected": bfs_inspected, "algorithmic_bytes": bytes_b,
