@@ -52,7 +52,8 @@ constexpr uint32_t CDLP_M_MAX = 512, CDLP_C_MAX = 4096;
 // can overlap.  One 1024-slot table per warp / 8192-slot table per CTA for all of M / C kept 24 warps per SM.
 constexpr uint32_t CDLP_M1_MAX = 128, CDLP_C1_MAX = 1024, CDLP_C2_MAX = 2048;
 constexpr uint32_t CDLP_PIECE = 4096;  // hub entries per CTA
-constexpr uint32_t CDLP_CT = 8192;     // slots of the CTA-wide shared-memory table (64 KB)
+constexpr uint32_t CDLP_CT = 8192;     // slots of the largest CTA-wide shared-memory table (64 KB): bin C3
+constexpr uint32_t CDLP_HCT = 2 * CDLP_PIECE; // slots of a hub piece's shared-memory table
 constexpr uint32_t CDLP_EPOCHS = 16, CDLP_CNT_MASK = 0x0FFFFFFFu; // 4-bit epoch tag above a 28-bit count
 
 struct CdlpPlan {
@@ -363,7 +364,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
                   uint2 *__restrict__ gtab, uint32_t epoch, unsigned long long *__restrict__ best_out)
 {
     extern __shared__ __align__(16) uint32_t s_tab[];
-    uint32_t *key = s_tab, *cnt = s_tab + CDLP_CT;
+    uint32_t *key = s_tab, *cnt = s_tab + CDLP_HCT;
     __shared__ unsigned long long s_best[CDLP_HT / 32];
     // dense iterations: one CTA per piece (piece_ids == NULL); sparse ones: the pieces of the active hub rows, listed and
     // counted on the device, drawn by a persistent grid
@@ -372,7 +373,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
         const uint32_t c = piece_ids ? piece_ids[ci] : ci;
         const uint32_t li = ins_row[c];
         const uint32_t v = listL[li];
-        for (uint32_t i = threadIdx.x; i < CDLP_CT; i += CDLP_HT) { key[i] = EMPTY; cnt[i] = 0; }
+        for (uint32_t i = threadIdx.x; i < CDLP_HCT; i += CDLP_HT) { key[i] = EMPTY; cnt[i] = 0; }
         __syncthreads();
         const bool side = ins_side[c] != 0;
         const uint64_t *rp = side ? rp1 : rp0;
@@ -387,7 +388,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
             cdlp_labels(col, 0, e_end, nullptr, 0, e_end, base + threadIdx.x, CDLP_HT, cur, lab);
 #pragma unroll
             for (int j = 0; j < CDLP_U; j++)
-                if (base + CDLP_HT * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_CT - 1, lab[j], lab[j] != EMPTY);
+                if (base + CDLP_HT * j + (threadIdx.x & ~31u) < e_end) warp_insert(key, cnt, CDLP_HCT - 1, lab[j], lab[j] != EMPTY);
         }
         __syncthreads();
         // The add that completes a label's count returns that count, so the largest (count, ~label) any add of
@@ -397,7 +398,7 @@ k_cdlp_big_insert(const uint32_t *__restrict__ listL, const uint32_t *__restrict
         // hundred distinct labels per piece most trips of the strided walk waited two dependent L2-miss atomics for one or two
         // lanes.  Then the target lines of all its (label, count) pairs are prefetched into L2, and only then come the
         // atomics: CDLP_U claims in flight per lane, then their adds (same 8-byte slot, now an L2 hit).
-        constexpr uint32_t SHARE = CDLP_CT / (CDLP_HT / 32);
+        constexpr uint32_t SHARE = CDLP_HCT / (CDLP_HT / 32);
         const unsigned lane = lane_id();
         uint32_t *wkey = key + (threadIdx.x >> 5) * SHARE, *wcnt = cnt + (threadIdx.x >> 5) * SHARE;
         uint32_t nw = 0;
@@ -773,7 +774,7 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
         constexpr size_t SMEM_C = (size_t)CDLP_CT * 8;
         GX_CUDA(cudaFuncSetAttribute(k_cdlp_warp_rows<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8));
         GX_CUDA(cudaFuncSetAttribute(k_cdlp_cta_rows<CDLP_CT, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
-        GX_CUDA(cudaFuncSetAttribute(k_cdlp_big_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_C));
+        GX_CUDA(cudaFuncSetAttribute(k_cdlp_big_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CDLP_HCT * 8)));
         g->res_u64.alloc(n);
         const uint64_t m_eff = g->directed ? 2 * g->m : g->m;
         const char *ae = getenv("GX_CDLP_ACTIVE"); // GX_CDLP_ACTIVE=0: recompute every row every iteration
@@ -822,7 +823,7 @@ extern "C" int gx_cdlp(gx_graph *g, int itermax, uint64_t *label_host)
                         p.gtab.zero();
                         p.epoch = 1;
                     }
-                    GX_LAUNCH(k_cdlp_big_insert, sparse ? grid_persistent(3) : (unsigned)p.n_ins, CDLP_HT, SMEM_C, p.listL.p, p.ins_row.p,
+                    GX_LAUNCH(k_cdlp_big_insert, sparse ? grid_persistent(3) : (unsigned)p.n_ins, CDLP_HT, CDLP_HCT * 8, p.listL.p, p.ins_row.p,
                               p.ins_side.p, p.ins_begin.p, p.tab_off.p, rp0, col0, rp1, col1, cur, sparse ? p.apieces.p : nullptr,
                               sparse ? p.acount.p + (CDLP_BINS - 1) : nullptr, (uint32_t)p.n_ins, p.gtab.p, p.epoch, p.best.p);
                     GX_LAUNCH(k_cdlp_big_final, grid_for(p.nL, 256), 256, 0, p.listL.p, p.nL, p.best.p, cur, nxt, act, changed);
