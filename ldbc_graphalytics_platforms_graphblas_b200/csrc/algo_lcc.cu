@@ -120,8 +120,14 @@ k_lcc_count(const uint64_t *__restrict__ orp, const uint32_t *__restrict__ ocol,
             const uint32_t owner = eowner[pos];
             if (threadIdx.x == 0) s_seg_end = run_end;
             __syncthreads();
+            // owners ascend along the list, so the segment's end is the one position whose owner differs while its
+            // predecessor's does not: a single writer (every thread beyond the end used to queue an atomicMin on the
+            // same shared word, ~250 serialised atomics per segment of a few dozen entries)
             for (uint64_t i = pos + 1 + threadIdx.x; i < run_end; i += 256)
-                if (eowner[i] != owner) { atomicMin(&s_seg_end, (unsigned long long)i); break; }
+                if (eowner[i] != owner) {
+                    if (eowner[i - 1] == owner) s_seg_end = i;
+                    break;
+                }
             const uint64_t t0 = tab_off[owner], tmask = tab_off[owner + 1] - t0; // table size (power of two) or 0
             const bool staged = tmask != 0 && tmask <= LCC_SMEM_SLOTS;
             if (staged)
