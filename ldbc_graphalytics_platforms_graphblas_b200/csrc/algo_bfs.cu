@@ -52,6 +52,39 @@ __device__ __forceinline__ void bfs_append(bool won, uint32_t v, uint32_t *next_
     if (won) next_q[base + __popc(mask & ((1u << lane_id()) - 1u))] = v;
 }
 
+// The same through a per-warp staging buffer in shared memory: the winners of several steps leave with one atomic on
+// the queue's cursor.  In the big level of a push-only search nearly every 32-edge step has a winner, and several
+// hundred thousand warp-steps queueing on one address cost more than the edges themselves.
+constexpr unsigned BFS_STAGE = 128; // entries per warp; flushed when fewer than 32 slots are left
+struct BfsStage {
+    uint32_t *buf;
+    unsigned n; // warp-uniform
+};
+__device__ __forceinline__ BfsStage bfs_stage()
+{
+    __shared__ uint32_t s_stage[32][BFS_STAGE]; // up to 32 warps per CTA
+    return BfsStage{s_stage[threadIdx.x >> 5], 0u};
+}
+__device__ __forceinline__ void bfs_stage_flush(BfsStage &st, uint32_t *next_q, BfsCounters *cnt)
+{
+    if (st.n == 0) return;
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(&cnt->next_count, (unsigned long long)st.n);
+    base = __shfl_sync(FULL, base, 0);
+    for (unsigned i = lane_id(); i < st.n; i += 32) next_q[base + i] = st.buf[i];
+    __syncwarp();
+    st.n = 0;
+}
+__device__ __forceinline__ void bfs_stage_append(BfsStage &st, bool won, uint32_t v, uint32_t *next_q, BfsCounters *cnt)
+{
+    const unsigned mask = __ballot_sync(FULL, won);
+    if (mask == 0) return;
+    if (won) st.buf[st.n + __popc(mask & ((1u << lane_id()) - 1u))] = v;
+    st.n += __popc(mask);
+    if (st.n > BFS_STAGE - 32) bfs_stage_flush(st, next_q, cnt);
+}
+
 __device__ __forceinline__ void
 bfs_push_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const uint32_t *__restrict__ queue,
                uint64_t qn, int32_t *__restrict__ level, int32_t depth, uint32_t *__restrict__ next_q,
@@ -60,6 +93,7 @@ bfs_push_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__
     uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long nf = 0, mf = 0;
+    BfsStage st = bfs_stage();
     for (; wid < qn; wid += nw) {
         const uint32_t u = queue[wid];
         const uint64_t a = rowptr[u], b = rowptr[u + 1];
@@ -80,9 +114,10 @@ bfs_push_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restrict__
                 won = bfs_claim(level, v, depth);
                 if (won) { nf++; mf += rowptr[v + 1] - rowptr[v]; }
             }
-            bfs_append(won, v, next_q, cnt);
+            bfs_stage_append(st, won, v, next_q, cnt);
         }
     }
+    bfs_stage_flush(st, next_q, cnt);
     nf = warp_sum(nf);
     mf = warp_sum(mf);
     if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
@@ -103,6 +138,7 @@ bfs_push_big_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restri
 {
     const unsigned long long nbig = cnt->big_count;
     unsigned long long nf = 0, mf = 0;
+    BfsStage st = bfs_stage();
     for (unsigned long long c = blockIdx.x; c < nbig; c += gridDim.x) {
         const uint64_t b0 = big_begin[c];
         const uint64_t row_end = rowptr[big_row[c] + 1];
@@ -116,9 +152,10 @@ bfs_push_big_phase(const uint64_t *__restrict__ rowptr, const uint32_t *__restri
                 won = bfs_claim(level, v, depth);
                 if (won) { nf++; mf += rowptr[v + 1] - rowptr[v]; }
             }
-            bfs_append(won, v, next_q, cnt);
+            bfs_stage_append(st, won, v, next_q, cnt);
         }
     }
+    bfs_stage_flush(st, next_q, cnt);
     nf = warp_sum(nf);
     mf = warp_sum(mf);
     if (lane_id() == 0 && nf) { atomicAdd(&cnt->nf, nf); atomicAdd(&cnt->mf, mf); }
