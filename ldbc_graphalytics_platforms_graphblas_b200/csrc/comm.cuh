@@ -1,12 +1,13 @@
 // comm.cuh -- multi-GPU plumbing: one process per GPU, NCCL over NVLink.
 //
-// Sharding model: every rank keeps the whole adjacency in its own HBM
-// (RMAT-26 symmetric + FP64 weights is ~26 GB of 180 GB), the ROWS are split into contiguous
-// blocks balanced by entry count, and the dense per-vertex state is replicated: after each
-// bulk-synchronous step the owned slices are all-gathered (PR ranks, CDLP labels, BFS frontier
-// bitmap) or the replicas min/sum-reduced (WCC parents, SSSP distances, LCC counts).
-// Getting the graph in follows the same idea in reverse: every rank is handed the same host arrays,
-// uploads 1/nranks of them over PCIe and receives the rest by all-gather over NVLink (graph.cu).
+// Sharding model: the ROWS are split into contiguous blocks balanced by entry count and a rank
+// computes the rows of its block.  The out-adjacency is on every rank (every process is handed the same host arrays,
+// uploads 1/nranks of them over PCIe and receives the rest by all-gather over NVLink, graph.cu); the in-adjacency is
+// row-partitioned (block-local transposition: a rank sorts and keeps the in-edge rows of its block only).  Per-vertex
+// state is exchanged after each bulk-synchronous step in the cheapest form that works for the algorithm: PageRank
+// pushes only the slots a consumer gathers into that consumer's compact vector (peer stores), SSSP forwards
+// improvements to the owner's distance by peer atomics, BFS all-reduces next-frontier words, CDLP all-gathers labels,
+// WCC / LCC reduce replicas; the small per-round scalars go through peer mailboxes (below) instead of NCCL.
 #pragma once
 
 #include <vector>
