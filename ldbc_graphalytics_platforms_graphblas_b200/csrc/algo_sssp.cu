@@ -353,6 +353,9 @@ __device__ __forceinline__ void block_compact4(unsigned take, uint64_t v4, uint3
 {
     __shared__ unsigned s_cnt[8];
     __shared__ unsigned long long s_base;
+    // most 1024-vertex blocks of a round hold nothing to take: one barrier settles that (the scans run over all n
+    // vertices every round and were a tenth of the run at half of the streaming rate)
+    if (!__syncthreads_or((int)take)) return;
     const unsigned lane = lane_id(), wib = threadIdx.x >> 5;
     const unsigned mine = __popc(take);
     unsigned incl = mine;
