@@ -74,8 +74,9 @@ int gx_graph_create_csr(gx_graph **g, uint64_t n, uint64_t nnz, const uint64_t *
 /* Same with 32-bit column ids (halves the upload; n <= 2^32 - 2). */
 int gx_graph_create_csr32(gx_graph **g, uint64_t n, uint64_t nnz, const uint64_t *rowptr,
                           const uint32_t *colidx, const double *weights, int directed);
-/* gx_graph_create_csr32 + gx_graph_cache(what) in one call -- what the wrappers' UploadGraph does right
- * after ReadMatrixMarket / LAGraph_Cached_AT (pr.cpp:58-59).  With GX_CACHE_AT on a directed graph on one
+/* gx_graph_create_csr32 + gx_graph_cache(what) in one call, for a caller that keeps the graph across several
+ * algorithms (the analogue of LAGraph_Cached_AT, pr.cpp:58-59, folded into the upload).  The drop-in binaries pass
+ * cache = 0 and let each algorithm build what it needs inside its timed window, as the reference does.  With GX_CACHE_AT on a directed graph on one
  * GPU the transposition is pipelined with the upload: the column ids travel in row-block chunks and
  * every chunk is validated, sorted by column and histogrammed while the next one is on the bus. */
 int gx_graph_create_csr32_cached(gx_graph **g, uint64_t n, uint64_t nnz, const uint64_t *rowptr,
