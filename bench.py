@@ -25,11 +25,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL's INFO log (communicator size, rings, NVLS) stays available to whoever launches this -- it goes to stderr so
-# that stdout carries the one JSON line; an NCCL_DEBUG / NCCL_DEBUG_FILE set by the launcher wins
-os.environ.setdefault("NCCL_DEBUG", "INFO")
-os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# NCCL's INFO log (communicator size, rings, NVLS) stays available to whoever launches this, and stdout carries the one
+# JSON line: unless the launcher chose a log file itself, every rank logs into a file of its own and copies the lines
+# to stderr when it is done (NCCL_DEBUG_FILE=/dev/stderr would re-open, i.e. truncate, a stderr that is redirected to
+# a file).  An NCCL_DEBUG / NCCL_DEBUG_SUBSYS / NCCL_DEBUG_FILE set by the launcher wins.
+# (The image exports NCCL_DEBUG=VERSION: that default is treated like "unset", an explicit WARN / INFO / TRACE is kept.)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+NCCL_LOG = None
+if "NCCL_DEBUG_FILE" not in os.environ:
+    NCCL_LOG = os.path.join(tempfile.gettempdir(), f"gx_nccl_{os.getpid()}.log")
+    os.environ["NCCL_DEBUG_FILE"] = NCCL_LOG
 
 PR_DAMPING, PR_ITERS = 0.85, 10
 BASE_SCALE, EDGEFACTOR = 22, 16
@@ -452,11 +459,33 @@ def run_gpu(args):
         sys.exit(1)
 
 
+def echo_nccl_log(limit=60):
+    """This rank's NCCL log (see NCCL_LOG above) copied to stderr: the init lines that name the communicator's size and
+    transport first, at most `limit` lines in all."""
+    if not NCCL_LOG:
+        return
+    try:
+        with open(NCCL_LOG, errors="replace") as f:
+            lines = [l.rstrip("\n") for l in f if l.strip()]
+        os.unlink(NCCL_LOG)
+    except OSError:
+        return
+    key = [l for l in lines if "nranks" in l or "NCCL version" in l or "NVLS" in l]
+    rest = [l for l in lines if l not in key]
+    if os.environ.get("RANK", "0") != "0":
+        limit = 8 # the other ranks: the communicator lines only
+    out = (key + rest)[:limit]
+    if out: # one write per rank: the ranks share the launcher's stderr
+        sys.stderr.write("\n".join(out) + "\n")
+        sys.stderr.flush()
+
+
 def shutdown(dist, before_exit=None):
     """The library's communicator goes first; rank 0 prints its line while the other ranks wait at the barrier, so
     nothing NCCL logs during the teardown can land in the middle of it."""
     from ldbc_graphalytics_platforms_graphblas_b200 import capi
     capi.comm_destroy()
+    echo_nccl_log()
     if dist is not None:
         dist.barrier()
     if before_exit is not None:
