@@ -36,7 +36,6 @@
 // -- on RMAT graphs iterations 5..10 touch ~5-15 % of the entries.  The labels are the same bit for bit: skipped
 // rows would have recomputed the value they already hold.
 // Algorithmic bytes per iteration: 4 m' + 8(n+1) [x2 directed] + 4n + 4n.
-#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
