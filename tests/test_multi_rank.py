@@ -255,6 +255,21 @@ while True:
     if not int(ch):
         break
 assert np.array_equal(f.astype(np.uint64), oracle.wcc(n, g.rowptr, g.colidx, True)), "sampled WCC"
+
+# PageRank's per-iteration sink-mass sum through the peer mailboxes (k_pr_tele_mail / peer_mail_sum_f64): every rank
+# deposits its partial, all ranks add the partials IN RANK ORDER -- the same bits everywhere (an all-reduce may
+# associate differently per rank count), and the exchange doubles as the iteration's barrier
+rng = np.random.default_rng(100 + rank)
+for it in range(20):
+    part = float(rng.random() * 10.0 ** rng.integers(-12, 3))
+    box = [None] * world
+    dist.all_gather_object(box, part)              # slot [r] of every rank's mailbox
+    total = 0.0
+    for r_ in range(world):
+        total += box[r_]
+    bits = [None] * world
+    dist.all_gather_object(bits, np.float64(total).tobytes())
+    assert all(b_ == bits[0] for b_ in bits), "rank-ordered mailbox sum differs between ranks"
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
